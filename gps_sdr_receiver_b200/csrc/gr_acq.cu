@@ -1,0 +1,398 @@
+// Fused acquisition kernel: raw I/Q -> Doppler wipe-off -> coherent fold -> FFT-2048
+// -> x conj(code spectrum) -> inverse FFT -> |.|^2 non-coherent accumulation ->
+// argmax / mean / std / second peak.  Only gr_acq_cell tuples leave the SM.
+//
+// Replaces, for a whole PRN x Doppler grid per launch,
+//   gpsrecv.demodDoppler   src/gpsrecv.py:232-235   (wipe-off, t = (n+1)/fs float32, phase 0)
+//   gpsrecv.sweepAllSats   src/gpsrecv.py:241-274   (sum of 1-ms FFTs / avg, x conj spectrum, ifft, abs)
+//   gpsrecv.findCodePhase  src/gpsrecv.py:217-227   (argmax, mean, population std, z)
+// and the generalisation BASELINE.json names (tcoh coherent x nnoncoh non-coherent).
+//
+// Work decomposition: one CTA (128 threads) = one (recording, Doppler bin, group of G
+// PRNs).  Per non-coherent interval the CTA wipes off and folds the tcoh 1-ms blocks in
+// the time domain (sum of FFTs = FFT of the sum), runs ONE forward FFT whose spectrum
+// stays in registers, and for each of its G PRNs multiplies by the conjugate code
+// spectrum (L2-resident table, coalesced), runs the inverse FFT and adds |c|^2 to a
+// register-resident accumulator (16 lags per thread per PRN).  Nothing but the final
+// 32-byte cell per (PRN, bin) is written to HBM.
+#include <stdio.h>
+#include <vector>
+
+#include "gr_fft2048.cuh"
+#include "gr_internal.h"
+
+struct gr_acq_plan {
+    int nprn, nbins, tcoh, nnoncoh, mode, in_format;
+    int32_t* d_prns;
+    float* d_w32;          // fl32(2*pi*f) per bin (python-float product rounded once, gpsrecv.py:233)
+    // staging for the host entry point
+    void* d_in;  size_t in_bytes;
+    gr_acq_cell* d_out; size_t out_bytes;
+    cudaStream_t stream;
+    int last_launches;
+};
+
+struct AcqArgs {
+    const void* samples;
+    long long rec_stride;      // samples
+    const int32_t* prns;
+    const float* w32;
+    int nprn, nbins, ngroups, tcoh, nnoncoh, mode;
+    float scale;               // 1 / (tcoh * 2048)
+    gr_acq_cell* out;
+    GrTables tab;
+};
+
+// reference sample conversion, gpsrecv.py:168-173: complex64 / 127.5 - (1+1j).
+// numpy divides complex64 by the real scalar as  re * fl32(1/127.5)  (Smith's algorithm
+// with zero imaginary divisor), then subtracts 1 -- two separately rounded float32 ops.
+__device__ __forceinline__ float u8_to_f32(unsigned int b) {
+    const float scl = 1.0f / 127.5f;
+    return __fsub_rn(__fmul_rn((float)b, scl), 1.0f);
+}
+
+template <int IN_FMT>
+__device__ __forceinline__ cf load_sample(const void* base, long long n) {
+    if (IN_FMT == GR_IN_U8IQ) {
+        const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(base) + n);
+        return cf{u8_to_f32(v.x), u8_to_f32(v.y)};
+    } else {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(base) + n);
+        return cf{v.x, v.y};
+    }
+}
+
+// t[n] = (n+1)/fs in float32 (gpsrecv.py:32-33), arg = fl32(w32 * t[n]) (+ phase 0)
+__device__ __forceinline__ float nco_arg(float w32, long long n) {
+    const float tsec = __fdiv_rn((float)(n + 1), GR_FS);
+    return __fmul_rn(w32, tsec);
+}
+
+struct BlockStat {
+    double sum, sum2;
+    float mx;
+    int idx;
+};
+
+// all 128 threads get the CTA-wide result
+__device__ __forceinline__ BlockStat block_stats(const float* st, int t, double* sh_d, float* sh_f, int* sh_i) {
+    float s = 0.f, s2 = 0.f, mx = -1.f;
+    int idx = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float v = st[j];
+        s += v;
+        s2 = fmaf(v, v, s2);
+        if (v > mx) { mx = v; idx = t + 128 * j; }
+    }
+    double ds = (double)s, ds2 = (double)s2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        ds2 += __shfl_xor_sync(0xffffffffu, ds2, o);
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (om > mx || (om == mx && oi < idx)) { mx = om; idx = oi; }
+    }
+    const int w = t >> 5;
+    if ((t & 31) == 0) { sh_d[w] = ds; sh_d[4 + w] = ds2; sh_f[w] = mx; sh_i[w] = idx; }
+    __syncthreads();
+    BlockStat r{0.0, 0.0, -1.f, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        r.sum += sh_d[k];
+        r.sum2 += sh_d[4 + k];
+        const float om = sh_f[k];
+        const int oi = sh_i[k];
+        if (om > r.mx || (om == r.mx && oi < r.idx)) { r.mx = om; r.idx = oi; }
+    }
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ float block_max(float v, int t, float* sh_f) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((t & 31) == 0) sh_f[t >> 5] = v;
+    __syncthreads();
+    const float r = fmaxf(fmaxf(sh_f[0], sh_f[1]), fmaxf(sh_f[2], sh_f[3]));
+    __syncthreads();
+    return r;
+}
+
+template <int G, int IN_FMT>
+__global__ void __launch_bounds__(GR_FFT_THREADS, 2) acq_kernel(const AcqArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf* smem = reinterpret_cast<cf*>(smem_raw);
+    __shared__ double sh_d[8];
+    __shared__ float sh_f[4];
+    __shared__ int sh_i[4];
+
+    const int t = threadIdx.x;
+    int id = blockIdx.x;
+    const int grp = id % a.ngroups; id /= a.ngroups;
+    const int bin = id % a.nbins;
+    const int rec = id / a.nbins;
+
+    // per-thread twiddles, constant for the whole kernel
+    cf tw1[16], tw2[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float2 u = a.tab.tw1[t * 16 + k];
+        const float2 v = a.tab.tw2[(t & 7) * 16 + k];
+        tw1[k] = cf{u.x, u.y};
+        tw2[k] = cf{v.x, v.y};
+    }
+
+    const float w32 = a.w32[bin];
+    const long long rec_off = (long long)rec * a.rec_stride;
+    const void* src = (IN_FMT == GR_IN_U8IQ)
+                          ? (const void*)(reinterpret_cast<const uchar2*>(a.samples) + rec_off)
+                          : (const void*)(reinterpret_cast<const float2*>(a.samples) + rec_off);
+
+    int prn[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int pi = grp * G + g;
+        prn[g] = pi < a.nprn ? a.prns[pi] : 0;
+    }
+
+    float acc[G][16];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[g][j] = 0.f;
+
+    for (int k = 0; k < a.nnoncoh; ++k) {
+        // ---- wipe-off + coherent fold of tcoh 1-ms blocks (time domain) ----
+        cf X[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) X[j] = cf{0.f, 0.f};
+        for (int i = 0; i < a.tcoh; ++i) {
+            const long long base = (long long)(k * a.tcoh + i) * GR_N;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const long long n = base + t + 128 * j;
+                const cf s = load_sample<IN_FMT>(src, n);
+                float sn, cs;
+                sincosf(nco_arg(w32, n), &sn, &cs);
+                // s * exp(-i arg)
+                X[j].x += s.x * cs + s.y * sn;
+                X[j].y += s.y * cs - s.x * sn;
+            }
+        }
+        fft2048<true>(X, smem, tw1, tw2, t);
+
+        // ---- per PRN: x conj(code spectrum), inverse FFT (swap form), accumulate ----
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (prn[g] == 0) continue;                       // uniform across the CTA
+            const float2* cs = a.tab.conjspec + (size_t)prn[g] * GR_N;
+            cf y[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float2 c = __ldg(cs + t + 128 * j);
+                // Y = X * conjC ; operand of the swap-form inverse = (Im Y, Re Y)
+                y[j].x = X[j].x * c.y + X[j].y * c.x;
+                y[j].y = X[j].x * c.x - X[j].y * c.y;
+            }
+            fft2048<true>(y, smem, tw1, tw2, t);
+            if (a.mode == GR_ACQ_POW) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[g][j] += y[j].x * y[j].x + y[j].y * y[j].y;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[g][j] += sqrtf(y[j].x * y[j].x + y[j].y * y[j].y);
+            }
+        }
+    }
+
+    // ---- reduce every PRN's 2048 lags to one cell ----
+    const float sc = (a.mode == GR_ACQ_POW) ? a.scale * a.scale : a.scale;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (prn[g] == 0) continue;
+        float st[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) st[j] = acc[g][j] * sc;
+        const BlockStat bs = block_stats(st, t, sh_d, sh_f, sh_i);
+        const int mx = bs.idx;
+        float sec = -1.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = t + 128 * j;
+            int d = n - mx;
+            d = d < 0 ? -d : d;
+            d = d > GR_N / 2 ? GR_N - d : d;
+            if (d > GR_SECOND_PEAK_GUARD) sec = fmaxf(sec, st[j]);
+        }
+        sec = block_max(sec, t, sh_f);
+        gr_acq_cell* cell = a.out + ((size_t)rec * a.nprn + (grp * G + g)) * a.nbins + bin;
+        const int lo = (mx + GR_N - 1) & (GR_N - 1), hi = (mx + 1) & (GR_N - 1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = t + 128 * j;
+            if (n == lo) cell->em1 = st[j];
+            if (n == hi) cell->ep1 = st[j];
+        }
+        if (t == 0) {
+            const double mean = bs.sum / GR_N;
+            double var = bs.sum2 / GR_N - mean * mean;
+            var = var > 0.0 ? var : 0.0;
+            const double sd = sqrt(var);
+            cell->mx = mx;
+            cell->peak = bs.mx;
+            cell->mean = (float)mean;
+            cell->std = (float)sd;
+            cell->z = (float)(((double)bs.mx - mean) / sd);
+            cell->second = sec;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+#define GR_ACQ_G 4
+
+extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* bin_hz, int nbins, int tcoh_ms,
+                                  int nnoncoh, int mode, int in_format, gr_acq_plan** plan) {
+    GR_REQUIRE_INIT();
+    if (!prns || !bin_hz || !plan || nprn < 1 || nbins < 1 || tcoh_ms < 1 || nnoncoh < 1 ||
+        (mode != GR_ACQ_ABS && mode != GR_ACQ_POW) || (in_format != GR_IN_U8IQ && in_format != GR_IN_CF32)) {
+        gr_set_error("gr_acq_plan_create: invalid argument");
+        return GR_ERR_ARG;
+    }
+    for (int i = 0; i < nprn; ++i)
+        if (prns[i] < 1 || prns[i] > GR_MAX_PRN) { gr_set_error("gr_acq_plan_create: prn %d out of range", prns[i]); return GR_ERR_ARG; }
+    gr_acq_plan* p = new gr_acq_plan();
+    p->nprn = nprn; p->nbins = nbins; p->tcoh = tcoh_ms; p->nnoncoh = nnoncoh; p->mode = mode; p->in_format = in_format;
+    p->d_in = nullptr; p->in_bytes = 0; p->d_out = nullptr; p->out_bytes = 0; p->last_launches = 0;
+    std::vector<float> w(nbins);
+    for (int b = 0; b < nbins; ++b) w[b] = (float)(2.0 * 3.141592653589793 * bin_hz[b]);   // 2*np.pi*freq, then weak -> float32
+    GR_CUDA(cudaSetDevice(gr_lib()->device));
+    GR_CUDA(cudaMalloc(&p->d_prns, nprn * sizeof(int32_t)));
+    GR_CUDA(cudaMalloc(&p->d_w32, nbins * sizeof(float)));
+    GR_CUDA(cudaMemcpy(p->d_prns, prns, nprn * sizeof(int32_t), cudaMemcpyHostToDevice));
+    GR_CUDA(cudaMemcpy(p->d_w32, w.data(), nbins * sizeof(float), cudaMemcpyHostToDevice));
+    GR_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    *plan = p;
+    return GR_OK;
+}
+
+extern "C" int gr_acq_plan_destroy(gr_acq_plan* p) {
+    if (!p) return GR_OK;
+    cudaFree(p->d_prns);
+    cudaFree(p->d_w32);
+    if (p->d_in) cudaFree(p->d_in);
+    if (p->d_out) cudaFree(p->d_out);
+    cudaStreamDestroy(p->stream);
+    delete p;
+    return GR_OK;
+}
+
+extern "C" int gr_acq_last_launches(const gr_acq_plan* p) { return p ? p->last_launches : 0; }
+
+extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, int64_t rec_stride,
+                              gr_acq_cell* d_out, void* stream) {
+    GR_REQUIRE_INIT();
+    if (!p || !d_samples || !d_out || nrec < 1) { gr_set_error("gr_acq_run_dev: invalid argument"); return GR_ERR_ARG; }
+    if (nrec > 1 && rec_stride < (int64_t)p->tcoh * p->nnoncoh * GR_N) {
+        gr_set_error("gr_acq_run_dev: rec_stride %lld shorter than one recording", (long long)rec_stride);
+        return GR_ERR_ARG;
+    }
+    AcqArgs a;
+    a.samples = d_samples;
+    a.rec_stride = rec_stride;
+    a.prns = p->d_prns;
+    a.w32 = p->d_w32;
+    a.nprn = p->nprn;
+    a.nbins = p->nbins;
+    a.ngroups = (p->nprn + GR_ACQ_G - 1) / GR_ACQ_G;
+    a.tcoh = p->tcoh;
+    a.nnoncoh = p->nnoncoh;
+    a.mode = p->mode;
+    a.scale = 1.0f / ((float)p->tcoh * (float)GR_N);
+    a.out = d_out;
+    a.tab = gr_lib()->tab;
+    const long long nblocks = (long long)nrec * p->nbins * a.ngroups;
+    if (nblocks > 0x7fffffffLL) { gr_set_error("gr_acq_run_dev: grid too large"); return GR_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    auto kern = p->in_format == GR_IN_U8IQ ? acq_kernel<GR_ACQ_G, GR_IN_U8IQ> : acq_kernel<GR_ACQ_G, GR_IN_CF32>;
+    GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_FFT_SMEM_BYTES));
+    kern<<<(unsigned)nblocks, GR_FFT_THREADS, GR_FFT_SMEM_BYTES, s>>>(a);
+    GR_CUDA(cudaGetLastError());
+    p->last_launches = 1;
+    return GR_OK;
+}
+
+extern "C" int gr_acq_run_host(gr_acq_plan* p, const void* h_samples, int nrec, int64_t rec_stride,
+                               gr_acq_cell* h_out) {
+    GR_REQUIRE_INIT();
+    if (!p || !h_samples || !h_out || nrec < 1) { gr_set_error("gr_acq_run_host: invalid argument"); return GR_ERR_ARG; }
+    GR_CUDA(cudaSetDevice(gr_lib()->device));
+    const size_t bps = p->in_format == GR_IN_U8IQ ? 2 : 8;
+    const size_t rec_len = (size_t)p->tcoh * p->nnoncoh * GR_N;
+    if (nrec > 1 && (size_t)rec_stride < rec_len) { gr_set_error("gr_acq_run_host: rec_stride too short"); return GR_ERR_ARG; }
+    const size_t nsamp = (size_t)(nrec - 1) * (size_t)rec_stride + rec_len;
+    const size_t in_bytes = nsamp * bps, out_bytes = (size_t)nrec * p->nprn * p->nbins * sizeof(gr_acq_cell);
+    if (in_bytes > p->in_bytes) {
+        if (p->d_in) cudaFree(p->d_in);
+        p->d_in = nullptr; p->in_bytes = 0;
+        GR_CUDA(cudaMalloc(&p->d_in, in_bytes));
+        p->in_bytes = in_bytes;
+    }
+    if (out_bytes > p->out_bytes) {
+        if (p->d_out) cudaFree(p->d_out);
+        p->d_out = nullptr; p->out_bytes = 0;
+        GR_CUDA(cudaMalloc((void**)&p->d_out, out_bytes));
+        p->out_bytes = out_bytes;
+    }
+    GR_CUDA(cudaMemcpyAsync(p->d_in, h_samples, in_bytes, cudaMemcpyHostToDevice, p->stream));
+    int rc = gr_acq_run_dev(p, p->d_in, nrec, rec_stride, p->d_out, (void*)p->stream);
+    if (rc != GR_OK) return rc;
+    GR_CUDA(cudaMemcpyAsync(h_out, p->d_out, out_bytes, cudaMemcpyDeviceToHost, p->stream));
+    GR_CUDA(cudaStreamSynchronize(p->stream));
+    return GR_OK;
+}
+
+// ---- debug hook: the CTA FFT on its own ------------------------------------------------------
+__global__ void __launch_bounds__(GR_FFT_THREADS) fft_debug_kernel(const float2* in, float2* out, int inverse, GrTables tab) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf* smem = reinterpret_cast<cf*>(smem_raw);
+    const int t = threadIdx.x;
+    cf tw1[16], tw2[16], v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float2 u = tab.tw1[t * 16 + k];
+        const float2 w = tab.tw2[(t & 7) * 16 + k];
+        tw1[k] = cf{u.x, u.y};
+        tw2[k] = cf{w.x, w.y};
+    }
+    const float2* src = in + (size_t)blockIdx.x * GR_N;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float2 s = src[t + 128 * j];
+        v[j] = inverse ? cf{s.y, s.x} : cf{s.x, s.y};
+    }
+    fft2048<true>(v, smem, tw1, tw2, t);
+    float2* dst = out + (size_t)blockIdx.x * GR_N;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dst[t + 128 * j] = inverse ? make_float2(v[j].y, v[j].x) : make_float2(v[j].x, v[j].y);
+}
+
+extern "C" int gr_debug_fft2048(const float* h_in, float* h_out, int batch, int inverse) {
+    GR_REQUIRE_INIT();
+    if (!h_in || !h_out || batch < 1) { gr_set_error("gr_debug_fft2048: invalid argument"); return GR_ERR_ARG; }
+    GR_CUDA(cudaSetDevice(gr_lib()->device));
+    float2 *d_in, *d_out;
+    const size_t bytes = (size_t)batch * GR_N * sizeof(float2);
+    GR_CUDA(cudaMalloc(&d_in, bytes));
+    GR_CUDA(cudaMalloc(&d_out, bytes));
+    GR_CUDA(cudaMemcpy(d_in, h_in, bytes, cudaMemcpyHostToDevice));
+    GR_CUDA(cudaFuncSetAttribute(fft_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_FFT_SMEM_BYTES));
+    fft_debug_kernel<<<batch, GR_FFT_THREADS, GR_FFT_SMEM_BYTES>>>(d_in, d_out, inverse, gr_lib()->tab);
+    GR_CUDA(cudaGetLastError());
+    GR_CUDA(cudaMemcpy(h_out, d_out, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return GR_OK;
+}

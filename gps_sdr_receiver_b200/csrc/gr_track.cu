@@ -1,0 +1,965 @@
+// Batched channel tracker: one CTA (128 threads) per tracked satellite, persistent over
+// `n_epochs` consecutive epochs, all loop state resident on the device.
+//
+// Replaces, for every channel of a bank in ONE launch,
+//   gpslib.SatStream.process         src/gpslib.py:1141-1210   (epoch state machine)
+//   SatStream.demodDoppler           src/gpslib.py:1343-1346   (NCO wipe-off, float32 time base)
+//   SatStream.cacodeCorr             src/gpslib.py:1315-1327   (sum of CORR_AVG 1-ms FFTs, x conj spectrum, |ifft|)
+//   SatStream.findCodePhase/fit      src/gpslib.py:1268-1304   (argmax, mean/std, sub-sample fit)
+//   SatStream.corrQuality            src/gpslib.py:1331-1339
+//   SatStream.decodeData             src/gpslib.py:1394-1446   (1-ms prompt integrate & dump, carry-over, edges)
+//   SatStream.phaseLockedLoop        src/gpslib.py:1215-1262
+//   SatStream.sweepFrequency/getCorrMax  src/gpslib.py:1350-1380 (per-channel re-acquisition)
+//   gpsrecv worker pool / satCalc    src/gpsrecv.py:300-417    (one OS process per channel -> one CTA per channel)
+//
+// Numerical design (DESIGN.md "tracking kernel"):
+//   * NCO factorisation.  The reference rotates sample n of the epoch by exp(-i(phi + w t_n)),
+//     t_n = (n+1)/fs.  With n = 2048 b + i this is  r_i * R_b,  r_i = exp(-i(phi + w (i+1)/fs)),
+//     R_b = exp(-i w b 1ms), and r_i = r_t * rho_j for i = t + 128 j.  So one epoch costs each
+//     thread two sincosf instead of N_CYC*16, the per-sample work is one complex FMA, and the
+//     coherent fold of the CORR_AVG blocks happens in the time domain (sum of FFTs = FFT of sum).
+//   * uint8 I/Q enters the FMAs as integer-valued floats; the affine map x = b/127.5 - 1 of the
+//     reader (gpsrecv.py:168-173) is applied once per sum:  sum x q = s sum b q - (1+i) sum q.
+//   * Prompt integration runs in "row-rotated" layout: thread t, row j handles sample
+//     128*(delay>>7) + 2048(k-1) + t + 128 j of pass k, so only row 0 straddles a code-period
+//     boundary; the true 1-ms sums are  S_k - B_k + B_{k+1}  (B = the part of row 0 before the
+//     boundary).  4 FMA per sample, coalesced loads, no divergence.
+//   * The loop filter (arctan discriminator, pi-unwrap, lock detector, DF FIFO), the correlation
+//     quality FIFO, the sweep state machine and the edge detector run in the same kernel; only a
+//     gr_epoch_out record per channel and epoch leaves the SM.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+#include "gr_fft2048.cuh"
+#include "gr_internal.h"
+
+#define GR_DF_CAP 128            // NO_SEC = 1024 // N_CYC <= 128  (N_CYC >= 8)
+#define GR_CL_CAP (60 * 128)     // CORRLST_NO = 60 * NO_SEC
+#define GR_TWO_PI_D 6.283185307179586
+#define GR_TWO_PI_F 6.2831855f   // float32(2*np.pi)
+#define GR_PI_F 3.1415927f       // float32(np.pi)
+
+// ---- per-channel state (device global memory) -------------------------------------------
+struct GrChanHot {
+    int32_t active, prn, rec, delay;
+    int32_t locked, sweep, sweep_req, freq_weak;      // freq_weak: FREQ is a python float (not np.float32)
+    int32_t std_weak, ms_time, edge0, edge_len;       // EDGES[0], len(EDGES)
+    int32_t rep_sweep, df_len, df_head, df_save_len;
+    int32_t freq_save_weak, cl_len, cl_head, cl_sum;  // CORRLST ring
+    int32_t cl_sum_last, carry_cnt, pad0, pad1;
+    int64_t prev_stream_no;
+    double freq, freq_save, std_dev, prev_signal;
+    double carry_re, carry_im;                         // sum of PREV_SAMPLES
+    double max_corr, corr_q, corr_l;
+    float phase, amplitude;
+};
+struct GrChan {
+    GrChanHot h;                 // scalars: cached in shared memory while the kernel runs
+    float df[GR_DF_CAP];         // DF FIFO (ring)
+    float df_save[GR_DF_CAP];
+    int8_t cl[GR_CL_CAP];        // CORRLST FIFO (ring) of +1/-1
+};
+
+struct gr_track_bank {
+    gr_track_cfg cfg;
+    GrChan* d_state;
+    int32_t* d_slots;
+    std::vector<int> slot_used;      // host mirror
+    std::vector<int> active;         // sorted active slots
+    bool slots_dirty;
+    cudaStream_t stream;             // for the host entry point
+    cudaStream_t last_stream;
+    void* d_in;  size_t in_bytes;
+    gr_epoch_out* d_out; size_t out_bytes;
+    int last_launches;
+};
+
+struct TrackArgs {
+    const void* samples;
+    long long rec_stride;   // samples
+    long long smp_time;     // SMP_TIME of the first epoch
+    int n_epochs, n_active;
+    const int32_t* slots;
+    GrChan* state;
+    gr_epoch_out* out;
+    gr_track_cfg cfg;
+    GrTables tab;
+};
+
+// ---- shared-memory scratch -------------------------------------------------------------------
+#define GR_PART_ROWS 17                                   // prompt passes staged per reduction round
+#define GR_TRACK_BUF_BYTES (GR_PART_ROWS * 128 * 16)      // 34816 >= GR_FFT_SMEM_BYTES; FFT buffers alias it
+
+struct TrackSmem {
+    GrChanHot H;                         // this channel's scalar state for the life of the kernel
+    float code[GR_N];                    // resampled C/A code of this PRN
+    cf rho[16];                          // exp(-i w 128 j / fs)
+    cf Rm[GR_MAX_NCYC + 2];              // Rm[k] = R_{k-1} = exp(-i w (k-1) ms), k = 0..n_cyc
+    float4 red[GR_MAX_NCYC + 2];         // reduced prompt rows: (S_k, B_k)
+    float4 xs[GR_MAX_NCYC + 2];          // (X_k, XB_k): affine-corrected, block-rotated
+    float qred[4][6];                    // per-warp sums of q: all rows, masked row 0, wrapped rows
+    double sh_d[8];
+    float sh_f[8];
+    int sh_i[8];
+    float nb[2];                         // corr[mx-1], corr[mx+1]
+    double pr_re[GR_MAX_PROMPT], pr_im[GR_MAX_PROMPT];   // prompt means (complex128 in the reference)
+    float ph[GR_MAX_PROMPT + 2];         // phase / realPhase
+    // epoch scalars (written by thread 0, read by all after a barrier)
+    float w32, phase32;
+    int branch_sweep, delay, corr_delay, n_prompt;
+    double z, code_phase, cmean, cstd;
+    float c3[3];
+};
+
+// ---- sample access ------------------------------------------------------------------------------
+template <int IN_FMT>
+__device__ __forceinline__ cf load_raw(const void* base, long long n) {
+    if (IN_FMT == GR_IN_U8IQ) {
+        const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(base) + n);
+        return cf{(float)v.x, (float)v.y};          // integer-valued; affine map applied per sum
+    } else {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(base) + n);
+        return cf{v.x, v.y};
+    }
+}
+
+// x = s*b - (1+i)  applied to a sum:  sum x q = s * sum(b q) - (1+i) * sum(q)
+template <int IN_FMT>
+__device__ __forceinline__ cf affine_sum(cf sb, cf sq) {
+    if (IN_FMT == GR_IN_U8IQ) {
+        const float s = 1.0f / 127.5f;
+        // (1+i) * (a+ib) = (a-b) + i(a+b)
+        return cf{fmaf(sb.x, s, -(sq.x - sq.y)), fmaf(sb.y, s, -(sq.x + sq.y))};
+    } else {
+        return sb;
+    }
+}
+
+__device__ __forceinline__ cf expmi(float a) {   // exp(-i a)
+    float s, c;
+    sincosf(a, &s, &c);
+    return cf{c, -s};
+}
+__device__ __forceinline__ cf expmi_d(double a) {   // exp(-i a), argument reduced in double
+    a -= GR_TWO_PI_D * rint(a / GR_TWO_PI_D);
+    return expmi((float)a);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- correlation: folded samples F (natural FFT layout) -> statistics of |ifft(fft(F)/avg * conjC)| --
+// Leaves mx in S->sh_i[4], z / mean / std / corr[mx-1..mx+1] in S; ends with a barrier.
+__device__ __forceinline__ void corr_and_stats(cf* F, const float2* __restrict__ cs, float scale, cf* fftbuf,
+                                               const cf* tw1, const cf* tw2, int t, TrackSmem* S) {
+    fft2048<true>(F, fftbuf, tw1, tw2, t);
+    cf y[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float2 c = __ldg(cs + t + 128 * j);
+        y[j].x = F[j].x * c.y + F[j].y * c.x;      // swap form of the inverse transform
+        y[j].y = F[j].x * c.x - F[j].y * c.y;
+    }
+    __syncthreads();                               // fftbuf is reused by the second transform
+    fft2048<true>(y, fftbuf, tw1, tw2, t);
+    float st[16];
+    float s = 0.f, s2 = 0.f, mx = -1.f;
+    int idx = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float v = sqrtf(y[j].x * y[j].x + y[j].y * y[j].y) * scale;
+        st[j] = v;
+        s += v;
+        s2 = fmaf(v, v, s2);
+        if (v > mx) { mx = v; idx = t + 128 * j; }
+    }
+    double ds = (double)s, ds2 = (double)s2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        ds2 += __shfl_xor_sync(0xffffffffu, ds2, o);
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (om > mx || (om == mx && oi < idx)) { mx = om; idx = oi; }
+    }
+    const int w = t >> 5;
+    if ((t & 31) == 0) { S->sh_d[w] = ds; S->sh_d[4 + w] = ds2; S->sh_f[w] = mx; S->sh_i[w] = idx; }
+    __syncthreads();
+    double sum = 0.0, sum2 = 0.0;
+    float bm = -1.f;
+    int bi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        sum += S->sh_d[k];
+        sum2 += S->sh_d[4 + k];
+        const float om = S->sh_f[k];
+        const int oi = S->sh_i[k];
+        if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
+    }
+    const int lo = (bi + GR_N - 1) & (GR_N - 1), hi = (bi + 1) & (GR_N - 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int n = t + 128 * j;
+        if (n == lo) S->nb[0] = st[j];
+        if (n == hi) S->nb[1] = st[j];
+    }
+    __syncthreads();
+    if (t == 0) {
+        const double mean = sum / GR_N;
+        double var = sum2 / GR_N - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        S->cmean = mean;
+        S->cstd = sqrt(var);
+        S->z = ((double)bm - mean) / S->cstd;
+        S->c3[0] = S->nb[0];
+        S->c3[1] = bm;
+        S->c3[2] = S->nb[1];
+        S->sh_i[4] = bi;
+    }
+    __syncthreads();
+}
+
+// gpslib.py:1268-1290 fitCodePhase (double arithmetic on the float32 correlation values)
+__device__ __forceinline__ double fit_code_phase(int mx, double lo, double c, double hi) {
+    double tri;
+    if (lo > hi) tri = 0.5 * (hi - lo) / (c - hi);
+    else tri = 0.5 * (hi - lo) / (c - lo);
+    const double par = 0.5 * (hi - lo) / (2.0 * c - hi - lo);
+    return (double)mx + 0.5 * (tri + par);
+}
+
+// Coherent fold of `nblk` 1-ms blocks starting at block `first` (natural FFT layout):
+//   F[j] = r_t rho_j * sum_b R_b x_b[t + 128 j]
+template <int IN_FMT>
+__device__ __forceinline__ void fold_blocks(cf* F, const void* src, int first, int nblk, cf rt, int t,
+                                            const TrackSmem* S) {
+    cf A[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) A[j] = cf{0.f, 0.f};
+    cf rsum = cf{0.f, 0.f};
+    for (int b = first; b < first + nblk; ++b) {
+        const cf R = S->Rm[b + 1];
+        rsum = cadd(rsum, R);
+        const long long base = (long long)b * GR_N + t;
+        cf x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = load_raw<IN_FMT>(src, base + 128 * j);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            A[j].x = fmaf(x[j].x, R.x, A[j].x);
+            A[j].x = fmaf(-x[j].y, R.y, A[j].x);
+            A[j].y = fmaf(x[j].x, R.y, A[j].y);
+            A[j].y = fmaf(x[j].y, R.x, A[j].y);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const cf r = cmul(rt, S->rho[j]);
+        F[j] = cmul(affine_sum<IN_FMT>(A[j], rsum), r);
+    }
+}
+
+// NCO tables of one wipe-off: rho_j, R_{k-1}; returns this thread's r_t.  Caller syncs.
+__device__ __forceinline__ cf nco_setup(float w32, float phase32, int n_cyc, int t, TrackSmem* S) {
+    if (t < 16) S->rho[t] = expmi_d((double)w32 * (double)(128 * t) / (double)GR_FS);
+    if (t >= 32 && t < 32 + n_cyc + 1) {
+        const int k = t - 32;
+        S->Rm[k] = expmi_d((double)w32 * (double)(k - 1) * 1e-3);
+    }
+    // a_t = fl32(phase + fl32(w * t_sec)),  t_sec = fl32((t+1)/fs)    (gpslib.py:1053-1054, 1344)
+    const float tsec = __fdiv_rn((float)(t + 1), GR_FS);
+    const float a = __fadd_rn(phase32, __fmul_rn(w32, tsec));
+    return expmi(a);
+}
+
+__device__ __forceinline__ float weak_w32(double freq, int weak) {
+    // 2*np.pi*freq: python-float product rounded once when FREQ is a python float,
+    // float32 product when FREQ is np.float32 (numpy 2 scalar promotion)
+    return weak ? (float)(GR_TWO_PI_D * freq) : __fmul_rn(GR_TWO_PI_F, (float)freq);
+}
+
+// ---- state helpers (thread 0; c = scalars in shared memory, g = rings in global memory) ------
+__device__ __forceinline__ void st_erase_prev(GrChanHot* c) {      // gpslib.py:1095-1099
+    c->edge0 = 0;
+    c->edge_len = 1;
+    c->carry_cnt = 0;
+    c->carry_re = 0.0;
+    c->carry_im = 0.0;
+}
+__device__ __forceinline__ void st_unlock(GrChanHot* c, GrChan* g) {          // gpslib.py:1102-1107
+    c->locked = 0;
+    c->cl_len = 1; c->cl_head = 0; g->cl[0] = 0; c->cl_sum = 0; c->cl_sum_last = 0;
+    c->ms_time = 0;
+    c->phase = 0.f;
+    st_erase_prev(c);
+}
+__device__ __forceinline__ void st_init_sweep(GrChanHot* c, GrChan* g, const gr_track_cfg& cfg) {   // gpslib.py:1110-1116
+    st_unlock(c, g);
+    c->freq_save = c->freq;
+    c->freq_save_weak = c->freq_weak;
+    c->df_save_len = c->df_len;
+    for (int i = 0; i < c->df_len; ++i) g->df_save[i] = g->df[(c->df_head + i) % GR_DF_CAP];
+    c->freq = (double)cfg.min_freq;
+    c->freq_weak = 1;
+    c->df_len = 1; c->df_head = 0; g->df[0] = 0.f;
+    c->sweep = 1;
+}
+// gpslib.py:1331-1339 corrQuality
+__device__ __forceinline__ void st_corr_quality(GrChanHot* c, GrChan* g, double code_phase, int no_sec) {
+    const int cap = 60 * no_sec;
+    const int8_t v = code_phase < 0.0 ? -1 : 1;
+    g->cl[(c->cl_head + c->cl_len) % GR_CL_CAP] = v;
+    c->cl_len += 1;
+    c->cl_sum += v;
+    c->cl_sum_last += v;
+    if (c->cl_len > no_sec) c->cl_sum_last -= g->cl[(c->cl_head + c->cl_len - 1 - no_sec) % GR_CL_CAP];
+    if (c->cl_len > cap) {
+        c->cl_sum -= g->cl[c->cl_head];
+        c->cl_head = (c->cl_head + 1) % GR_CL_CAP;
+        c->cl_len -= 1;
+    }
+    c->corr_q = (double)c->cl_sum / (double)c->cl_len;
+    const int nl = c->cl_len < no_sec ? c->cl_len : no_sec;
+    c->corr_l = (double)c->cl_sum_last / (double)nl;
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------
+template <int IN_FMT>
+__global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf* fftbuf = reinterpret_cast<cf*>(smem_raw);
+    float4* part = reinterpret_cast<float4*>(smem_raw);          // aliases the FFT buffers
+    TrackSmem* S = reinterpret_cast<TrackSmem*>(smem_raw + GR_TRACK_BUF_BYTES);
+    GrChanHot* C = &S->H;
+
+    const int t = threadIdx.x;
+    const int slot = a.slots[blockIdx.x];
+    GrChan* G = a.state + slot;
+    const int n_cyc = a.cfg.n_cyc;
+    const int ngps = n_cyc * GR_N;
+    const int no_sec = 1024 / n_cyc;
+    const int corr_avg = a.cfg.corr_avg < n_cyc ? a.cfg.corr_avg : n_cyc;
+    const int prn = G->h.prn;
+    const float2* cs = a.tab.conjspec + (size_t)prn * GR_N;
+
+    cf tw1[16], tw2[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float2 u = a.tab.tw1[t * 16 + k];
+        const float2 v = a.tab.tw2[(t & 7) * 16 + k];
+        tw1[k] = cf{u.x, u.y};
+        tw2[k] = cf{v.x, v.y};
+    }
+    for (int i = t; i < GR_N; i += GR_FFT_THREADS) S->code[i] = a.tab.code[(size_t)prn * GR_N + i];
+    if (t == 0) *C = G->h;
+    __syncthreads();
+
+    const long long rec_off = (long long)C->rec * a.rec_stride;
+    const char* rec_base = reinterpret_cast<const char*>(a.samples) + rec_off * (IN_FMT == GR_IN_U8IQ ? 2 : 8);
+
+    for (int e = 0; e < a.n_epochs; ++e) {
+        const void* src = rec_base + (long long)e * ngps * (IN_FMT == GR_IN_U8IQ ? 2 : 8);
+        const long long smp_time = a.smp_time + (long long)e * ngps;
+        const long long stream_no = smp_time / ngps;
+        gr_epoch_out* O = a.out + ((size_t)e * a.n_active + blockIdx.x);
+        const bool report = (stream_no % no_sec) == 0;
+
+        // ---- epoch prologue (gpslib.py:1142-1151) ----
+        if (t == 0) {
+            int erased = 0;
+            if (stream_no - 1 != C->prev_stream_no) { st_erase_prev(C); erased = 1; }
+            C->prev_stream_no = stream_no;
+            const int req = C->sweep_req && !C->sweep;
+            C->sweep_req = 0;
+            if (req) { st_init_sweep(C, G, a.cfg); erased = 1; }
+            O->erased = erased;
+            S->branch_sweep = C->sweep;
+            S->w32 = weak_w32(C->freq, C->freq_weak);
+            S->phase32 = C->phase;
+            O->edge_mask = 0ull;
+            O->n_prompt = 0;
+            O->prompt_b1 = 0;
+            O->prompt_st0 = 0;
+            O->locked_in = C->locked;
+            O->report_freq = 0.0;
+            O->rep_sweep = 0;
+            O->report = report ? 1 : 0;
+            O->prn = prn;
+        }
+        __syncthreads();
+
+        if (S->branch_sweep) {
+            // =============== sweep branch (gpslib.py:1153-1173, 1350-1380) ===============
+            int delay = -1;
+            double code_phase = -1.0, z = 0.0;
+            double freq = C->freq;                           // a python float during a sweep
+            const int avg = a.cfg.sweep_corr_avg;
+            int j = 0;
+            while (delay < 0 && j < a.cfg.it_sweep) {
+                const float w32 = (float)(GR_TWO_PI_D * freq);
+                const cf rt = nco_setup(w32, 0.f, n_cyc, t, S);
+                __syncthreads();
+                cf F[16];
+                fold_blocks<IN_FMT>(F, src, 0, avg, rt, t, S);
+                corr_and_stats(F, cs, 1.0f / ((float)avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
+                z = S->z;
+                if (z > (double)a.cfg.corr_min) {
+                    delay = S->sh_i[4];
+                    code_phase = fit_code_phase(delay, (double)S->c3[0], (double)S->c3[1], (double)S->c3[2]);
+                } else {
+                    freq = freq + (double)a.cfg.step_freq;
+                }
+                ++j;
+                __syncthreads();                              // S->z / rho / Rm are rewritten next round
+            }
+            int running = 1;
+            if (delay >= 0) running = 0;
+            else if (freq > (double)a.cfg.max_freq) { freq = (double)a.cfg.min_freq; running = 0; }
+            if (t == 0) {
+                C->rep_sweep = 1;
+                C->sweep = running;
+                C->freq = freq;
+                C->freq_weak = 1;
+                C->max_corr = z;
+                st_corr_quality(C, G, code_phase, no_sec);
+                if (delay >= 0) C->delay = delay;
+                else if (!running) {                          // restoreFreq, gpslib.py:1118-1120
+                    C->freq = C->freq_save;
+                    C->freq_weak = C->freq_save_weak;
+                    C->df_len = C->df_save_len;
+                    C->df_head = 0;
+                    for (int i = 0; i < C->df_len; ++i) G->df[i] = G->df_save[i];
+                }
+                O->tracked = 0;
+                O->corr_delay = delay;
+                O->code_phase = code_phase;
+                if (report) { O->rep_sweep = C->rep_sweep; O->report_freq = C->freq; C->rep_sweep = 0; }
+                O->corr3[0] = S->c3[0]; O->corr3[1] = S->c3[1]; O->corr3[2] = S->c3[2];
+                O->corr_mean = (float)S->cmean;
+                O->corr_std = (float)S->cstd;
+            }
+        } else {
+            // =============== tracking branch (gpslib.py:1175-1208) ===============
+            const float w32 = S->w32, phase32 = S->phase32;
+            const cf rt = nco_setup(w32, phase32, n_cyc, t, S);
+            __syncthreads();
+            {
+                cf F[16];
+                fold_blocks<IN_FMT>(F, src, (n_cyc - corr_avg) / 2, corr_avg, rt, t, S);
+                corr_and_stats(F, cs, 1.0f / ((float)corr_avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
+            }
+            if (t == 0) {
+                int delay = -1;
+                double code_phase = -1.0;
+                if (S->z > (double)a.cfg.corr_min) {
+                    delay = S->sh_i[4];
+                    code_phase = fit_code_phase(delay, (double)S->c3[0], (double)S->c3[1], (double)S->c3[2]);
+                }
+                st_corr_quality(C, G, code_phase, no_sec);
+                if (delay >= 0) C->delay = delay;
+                S->corr_delay = delay;
+                S->code_phase = code_phase;
+                S->delay = C->delay;
+            }
+            __syncthreads();
+
+            // ---- prompt integrate & dump (decodeData) in row-rotated layout ----
+            const int d = S->delay;
+            const int jb = d >> 7, dlow = d & 127;
+            const bool inB = t < dlow;                       // row 0, before the code-period boundary
+            cf q[16];
+            {
+                cf qall = cf{0.f, 0.f}, qw = cf{0.f, 0.f};
+                const cf R1 = S->Rm[2];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int row = (j + jb) & 15;
+                    const bool wrapped = (j + jb) >= 16;
+                    const int i = t + 128 * row;
+                    const float c = S->code[(i - d) & (GR_N - 1)];
+                    cf r = cmul(rt, S->rho[row]);
+                    if (wrapped) r = cmul(r, R1);
+                    q[j] = cf{r.x * c, r.y * c};
+                    qall = cadd(qall, q[j]);
+                    if (wrapped) qw = cadd(qw, q[j]);
+                }
+                float v[6] = {qall.x, qall.y, inB ? q[0].x : 0.f, inB ? q[0].y : 0.f, qw.x, qw.y};
+#pragma unroll
+                for (int m = 0; m < 6; ++m) {
+                    v[m] = warp_sum(v[m]);
+                    if ((t & 31) == 0) S->qred[t >> 5][m] = v[m];
+                }
+            }
+            for (int k0 = 0; k0 <= n_cyc; k0 += GR_PART_ROWS) {
+                const int k1 = (k0 + GR_PART_ROWS <= n_cyc + 1) ? k0 + GR_PART_ROWS : n_cyc + 1;
+                for (int k = k0; k < k1; ++k) {
+                    const long long base = (long long)128 * jb + (long long)GR_N * (k - 1) + t;
+                    cf x[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const bool wrapped = (j + jb) >= 16;
+                        const bool valid = (k == 0) ? wrapped : (k == n_cyc ? !wrapped : true);
+                        x[j] = valid ? load_raw<IN_FMT>(src, base + 128 * j) : cf{0.f, 0.f};
+                    }
+                    cf p0 = cmul(x[0], q[0]);
+                    cf acc = p0;
+#pragma unroll
+                    for (int j = 1; j < 16; ++j) {
+                        acc.x = fmaf(x[j].x, q[j].x, acc.x);
+                        acc.x = fmaf(-x[j].y, q[j].y, acc.x);
+                        acc.y = fmaf(x[j].x, q[j].y, acc.y);
+                        acc.y = fmaf(x[j].y, q[j].x, acc.y);
+                    }
+                    if (!inB) p0 = cf{0.f, 0.f};
+                    part[(k - k0) * 128 + t] = make_float4(acc.x, acc.y, p0.x, p0.y);
+                }
+                __syncthreads();
+                {   // reduce the staged rows: warp w takes rows w, w+4, ...
+                    const int w = t >> 5, l = t & 31;
+                    for (int r = w; r < k1 - k0; r += 4) {
+                        float4 v = part[r * 128 + l];
+#pragma unroll
+                        for (int m = 1; m < 4; ++m) {
+                            const float4 u = part[r * 128 + l + 32 * m];
+                            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+                        }
+                        v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
+                        if (l == 0) S->red[k0 + r] = v;
+                    }
+                }
+                __syncthreads();
+            }
+            // true-sample sums X_k, XB_k (threads 0..n_cyc), then the per-ms means (thread 0)
+            if (t <= n_cyc) {
+                const int k = t;
+                const float4 v = S->red[k];
+                float qs[6];
+#pragma unroll
+                for (int m = 0; m < 6; ++m) qs[m] = (S->qred[0][m] + S->qred[1][m]) + (S->qred[2][m] + S->qred[3][m]);
+                const cf Qk = (k == 0) ? cf{qs[4], qs[5]} : (k == n_cyc ? cf{qs[0] - qs[4], qs[1] - qs[5]} : cf{qs[0], qs[1]});
+                cf X = affine_sum<IN_FMT>(cf{v.x, v.y}, Qk);
+                cf XB = (k == 0) ? cf{0.f, 0.f} : affine_sum<IN_FMT>(cf{v.z, v.w}, cf{qs[2], qs[3]});
+                const cf R = S->Rm[k];
+                X = cmul(X, R);
+                XB = cmul(XB, R);
+                S->xs[k] = make_float4(X.x, X.y, XB.x, XB.y);
+            }
+            __syncthreads();
+            if (t == 0) {
+                // seg_m = X_m - XB_m + XB_{m+1} (m < n_cyc), tail = X_n - XB_n
+                const int nps = C->carry_cnt;
+                int n1 = nps + d;
+                long long st;
+                if (n1 == 0) { n1 = GR_N; st = smp_time; } else { st = smp_time + d - GR_N; }
+                int np = 0;
+                const double cre = C->carry_re, cim = C->carry_im;
+                for (int m = 0; m <= n_cyc; ++m) {
+                    const float4 v = S->xs[m];
+                    double sre = (double)v.x - (double)v.z, sim = (double)v.y - (double)v.w;
+                    if (m < n_cyc) { const float4 u = S->xs[m + 1]; sre += (double)u.z; sim += (double)u.w; }
+                    if (m == 0) {
+                        const int cnt = nps + d;
+                        if (cnt > 0) {
+                            S->pr_re[np] = (cre + sre) / (double)cnt;
+                            S->pr_im[np] = (cim + sim) / (double)cnt;
+                            ++np;
+                        }
+                    } else if (m < n_cyc || d == 0) {
+                        S->pr_re[np] = sre / (double)GR_N;
+                        S->pr_im[np] = sim / (double)GR_N;
+                        ++np;
+                        if (m == n_cyc) { C->carry_cnt = 0; C->carry_re = 0.0; C->carry_im = 0.0; }
+                    } else {
+                        C->carry_cnt = GR_N - d;
+                        C->carry_re = sre;
+                        C->carry_im = sim;
+                    }
+                }
+                S->n_prompt = np;
+                // ---- edge detector (gpslib.py:1417-1436), threshold from the PREVIOUS epoch's STD_DEV ----
+                unsigned long long mask = 0ull;
+                if (C->locked) {
+                    const double min_edge = C->std_weak ? 3.0 * C->std_dev : (double)__fmul_rn(3.0f, (float)C->std_dev);
+                    int edge0 = C->edge0, elen = C->edge_len;
+                    double prev_sign = (double)((2 * (elen % 2) - 1) * edge0);
+                    double prev_signal = C->prev_signal;
+                    for (int k = 0; k < np; ++k) {
+                        const double mr = S->pr_re[k];
+                        const double s = mr > 0.0 ? 1.0 : (mr < 0.0 ? -1.0 : 0.0);
+                        if (edge0 == 0) {
+                            edge0 = (int)s;
+                            prev_sign = s;
+                        } else if (s != prev_sign && prev_sign * prev_signal > 0.0 && fabs(mr - prev_signal) > min_edge) {
+                            mask |= 1ull << k;
+                            ++elen;
+                            prev_sign = s;
+                        }
+                        prev_signal = mr;
+                    }
+                    C->edge0 = edge0;
+                    C->edge_len = elen;
+                    C->prev_signal = prev_signal;
+                    C->ms_time += np;
+                }
+                O->edge_mask = mask;
+                O->n_prompt = np;
+                O->prompt_b1 = n1;
+                O->prompt_st0 = st;
+            }
+            __syncthreads();
+
+            // ---- amplitude statistics + PLL (warp 0), gpslib.py:1186-1188, 1215-1262 ----
+            if (t < 32) {
+                const int np = S->n_prompt;
+                float ph[2], ab[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = t + 32 * h;
+                    ph[h] = 0.f; ab[h] = 0.f;
+                    if (k < np) {
+                        const cf g = cf{(float)S->pr_re[k], (float)S->pr_im[k]};      // np.asarray(..., complex64)
+                        O->prompt[2 * k] = g.x;
+                        O->prompt[2 * k + 1] = g.y;
+                        ph[h] = atanf(__fdiv_rn(g.y, g.x));
+                        ab[h] = hypotf(g.x, g.y);
+                        S->ph[k] = ph[h];
+                    }
+                }
+                __syncwarp();
+                // unwrap: dp -= sign(delta) whenever |delta| > 2; realPhase[i] += dp*pi
+                float inc[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = t + 32 * h;
+                    inc[h] = 0.f;
+                    if (k >= 1 && k < np) {
+                        const float dl = __fsub_rn(ph[h], S->ph[k - 1]);
+                        if (fabsf(dl) > 2.0f) inc[h] = dl > 0.f ? -1.f : 1.f;
+                    }
+                }
+                float sc = inc[0];                       // inclusive scan: elements 0..31
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float u = __shfl_up_sync(0xffffffffu, sc, o);
+                    if (t >= o) sc += u;
+                }
+                const float tot31 = __shfl_sync(0xffffffffu, sc, 31);
+                const float inc32 = __shfl_sync(0xffffffffu, inc[1], 0);
+                float turns[2];
+                turns[0] = sc;
+                turns[1] = tot31 + inc32 + (t == 1 ? inc[1] : 0.f);     // element 32 (lane 0), 33 (lane 1)
+                __syncwarp();
+                float sum_rp = 0.f, sum_ab = 0.f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = t + 32 * h;
+                    if (k < np) {
+                        const float rp = __fadd_rn(ph[h], __fmul_rn(turns[h], GR_PI_F));
+                        S->ph[k] = rp;
+                        sum_rp += rp;
+                        sum_ab += ab[h];
+                    }
+                }
+                sum_rp = warp_sum(sum_rp);
+                sum_ab = warp_sum(sum_ab);
+                const float fn = (float)np;
+                const float mean_ab = sum_ab / fn;
+                float sq = 0.f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = t + 32 * h;
+                    if (k < np) { const float dv = ab[h] - mean_ab; sq = fmaf(dv, dv, sq); }
+                }
+                sq = warp_sum(sq);
+                // mean of the DF FIFO
+                float dsum = 0.f;
+                const int dfl = C->df_len, dfh = C->df_head;
+                for (int i = t; i < dfl; i += 32) dsum += G->df[(dfh + i) % GR_DF_CAP];
+                dsum = warp_sum(dsum);
+                __syncwarp();
+                if (t == 0) {
+                    const float std32 = sqrtf(sq / fn);
+                    C->std_dev = (double)std32;
+                    C->std_weak = 0;
+                    C->amplitude = mean_ab / std32;
+                    C->max_corr = S->z;
+                    O->tracked = 1;
+                    O->corr_delay = S->corr_delay;
+                    O->code_phase = S->code_phase;
+                    O->corr3[0] = S->c3[0]; O->corr3[1] = S->c3[1]; O->corr3[2] = S->c3[2];
+                    O->corr_mean = (float)S->cmean;
+                    O->corr_std = (float)S->cstd;
+                    bool sweep = false;
+                    if (report) {
+                        O->rep_sweep = C->rep_sweep;
+                        O->report_freq = C->freq;
+                        C->rep_sweep = 0;
+                        if (C->locked && C->edge_len > 2) {          // evalEdges -> logicalBits, gpslib.py:1465-1487
+                            if ((C->edge_len - 2) & 1) C->edge0 = -C->edge0;
+                            C->edge_len = 2;
+                        }
+                        if (C->cl_len >= 60 * no_sec) sweep = C->corr_q < -0.9;   // checkCorrQuality
+                    }
+                    if (sweep) {
+                        st_init_sweep(C, G, a.cfg);
+                        O->erased |= 2;
+                    } else {
+                        // phaseLockedLoop
+                        const float max_df = 20.0f / (float)no_sec;
+                        const float dev = sum_rp / fn;
+                        const int n4 = np < 4 ? np : 4;
+                        float off = 0.f;
+                        for (int i = np - n4; i < np; ++i) off += S->ph[i];
+                        off = off / (float)n4;
+                        float df;
+                        if (C->locked) {
+                            df = __fadd_rn(dev, dsum / (float)dfl);
+                            if (fabsf(df) > max_df) df = df > 0.f ? max_df : -max_df;
+                            if (C->df_len >= no_sec) { C->df_head = (C->df_head + 1) % GR_DF_CAP; C->df_len -= 1; }
+                            G->df[(C->df_head + C->df_len) % GR_DF_CAP] = df;
+                            C->df_len += 1;
+                        } else {
+                            df = __fmul_rn(10.0f, dev);
+                            C->df_len = 1; C->df_head = 0; G->df[0] = df;
+                        }
+                        if (fabsf(dev) < 0.1f) C->locked = 1;
+                        // demodDoppler's phase carry (gpslib.py:1345-1346), then PHASE += phaseshift
+                        const float tlast = __fdiv_rn((float)ngps, GR_FS);
+                        float p = __fadd_rn(phase32, __fmul_rn(w32, tlast));
+                        p = fmodf(p, GR_TWO_PI_F);
+                        if (p < 0.f) p += GR_TWO_PI_F;
+                        C->phase = __fadd_rn(p, off);
+                        const float f = __fadd_rn((float)C->freq, df);
+                        if (f > a.cfg.max_freq) { C->freq = (double)a.cfg.max_freq; C->freq_weak = 1; }
+                        else if (f < a.cfg.min_freq) { C->freq = (double)a.cfg.min_freq; C->freq_weak = 1; }
+                        else { C->freq = (double)f; C->freq_weak = 0; }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (t == 0) {
+            O->sweep = C->sweep;
+            O->delay = C->delay;
+            O->locked = C->locked;
+            O->ms_time = C->ms_time;
+            O->n_prev = C->carry_cnt;
+            O->max_corr = C->max_corr;
+            O->corr_q = C->corr_q;
+            O->corr_l = C->corr_l;
+            O->freq = C->freq;
+            O->freq_weak = C->freq_weak;
+            O->edge0 = C->edge0;
+            O->edge_len = C->edge_len;
+            O->phase = (double)C->phase;
+            O->amplitude = C->amplitude;
+            O->std_dev = (float)C->std_dev;
+        }
+        __syncthreads();
+    }
+    if (t == 0) G->h = *C;
+}
+
+// ---- host API ------------------------------------------------------------------------------------------
+static size_t track_smem_bytes() { return GR_TRACK_BUF_BYTES + sizeof(TrackSmem); }
+
+extern "C" int gr_track_default_cfg(gr_track_cfg* cfg) {
+    if (!cfg) { gr_set_error("gr_track_default_cfg: null"); return GR_ERR_ARG; }
+    cfg->n_cyc = 32;            // gpsglob.py:122
+    cfg->corr_avg = 8;          // gpsglob.py:68
+    cfg->sweep_corr_avg = 4;    // gpsglob.py:71
+    cfg->it_sweep = 40;         // gpsglob.py:41
+    cfg->corr_min = 8.0f;       // gpsglob.py:69
+    cfg->min_freq = -5000.0f;   // gpsglob.py:63-64
+    cfg->max_freq = 5000.0f;
+    cfg->step_freq = 200.0f;    // gpsglob.py:65
+    cfg->in_format = GR_IN_U8IQ;
+    cfg->max_channels = 16;
+    return GR_OK;
+}
+
+extern "C" int gr_track_bank_create(const gr_track_cfg* cfg, gr_track_bank** bank) {
+    GR_REQUIRE_INIT();
+    if (!cfg || !bank) { gr_set_error("gr_track_bank_create: null argument"); return GR_ERR_ARG; }
+    if (cfg->n_cyc < 8 || cfg->n_cyc > GR_MAX_NCYC || (1024 % cfg->n_cyc) != 0 || cfg->corr_avg < 1 ||
+        cfg->sweep_corr_avg < 1 || cfg->sweep_corr_avg > cfg->n_cyc || cfg->it_sweep < 1 || cfg->max_channels < 1 ||
+        (cfg->in_format != GR_IN_U8IQ && cfg->in_format != GR_IN_CF32)) {
+        gr_set_error("gr_track_bank_create: invalid configuration (n_cyc must be 8, 16 or 32)");
+        return GR_ERR_ARG;
+    }
+    GR_CUDA(cudaSetDevice(gr_lib()->device));
+    gr_track_bank* b = new gr_track_bank();
+    b->cfg = *cfg;
+    b->slot_used.assign(cfg->max_channels, 0);
+    b->slots_dirty = true;
+    b->d_in = nullptr; b->in_bytes = 0; b->d_out = nullptr; b->out_bytes = 0; b->last_launches = 0;
+    b->last_stream = nullptr;
+    GR_CUDA(cudaMalloc((void**)&b->d_state, sizeof(GrChan) * (size_t)cfg->max_channels));
+    GR_CUDA(cudaMemset(b->d_state, 0, sizeof(GrChan) * (size_t)cfg->max_channels));
+    GR_CUDA(cudaMalloc((void**)&b->d_slots, sizeof(int32_t) * (size_t)cfg->max_channels));
+    GR_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)track_smem_bytes()));
+    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_CF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)track_smem_bytes()));
+    *bank = b;
+    return GR_OK;
+}
+
+extern "C" int gr_track_bank_destroy(gr_track_bank* b) {
+    if (!b) return GR_OK;
+    cudaDeviceSynchronize();
+    cudaFree(b->d_state);
+    cudaFree(b->d_slots);
+    if (b->d_in) cudaFree(b->d_in);
+    if (b->d_out) cudaFree(b->d_out);
+    cudaStreamDestroy(b->stream);
+    delete b;
+    return GR_OK;
+}
+
+static int bank_quiesce(gr_track_bank* b) {
+    // state edits from the host must not race a process call still in flight
+    GR_CUDA(cudaStreamSynchronize(b->last_stream));
+    return GR_OK;
+}
+
+extern "C" int gr_track_add(gr_track_bank* b, int rec, int prn, double freq, int delay) {
+    GR_REQUIRE_INIT();
+    if (!b || prn < 1 || prn > GR_MAX_PRN || rec < 0 || delay < 0 || delay >= GR_N) {
+        gr_set_error("gr_track_add: invalid argument (prn %d rec %d delay %d)", prn, rec, delay);
+        return GR_ERR_ARG;
+    }
+    int slot = -1;
+    for (size_t i = 0; i < b->slot_used.size(); ++i)
+        if (!b->slot_used[i]) { slot = (int)i; break; }
+    if (slot < 0) { gr_set_error("gr_track_add: bank full (%d channels)", (int)b->slot_used.size()); return GR_ERR_STATE; }
+    int rc = bank_quiesce(b);
+    if (rc != GR_OK) return rc;
+    static GrChan c;                      // gpslib.py:1050-1091
+    memset(&c, 0, sizeof(c));
+    c.h.active = 1; c.h.prn = prn; c.h.rec = rec; c.h.delay = delay;
+    c.h.freq = freq; c.h.freq_weak = 1;
+    c.h.std_dev = 0.005; c.h.std_weak = 1;
+    c.h.edge0 = 0; c.h.edge_len = 1;
+    c.h.df_len = 1; c.h.df_head = 0; c.df[0] = 0.f;
+    c.h.cl_len = 1; c.h.cl_head = 0; c.cl[0] = 0;
+    c.h.prev_stream_no = 0;
+    GR_CUDA(cudaMemcpy(b->d_state + slot, &c, sizeof(GrChan), cudaMemcpyHostToDevice));
+    b->slot_used[slot] = 1;
+    b->slots_dirty = true;
+    return slot;
+}
+
+extern "C" int gr_track_remove(gr_track_bank* b, int slot) {
+    GR_REQUIRE_INIT();
+    if (!b || slot < 0 || slot >= (int)b->slot_used.size() || !b->slot_used[slot]) {
+        gr_set_error("gr_track_remove: invalid slot %d", slot);
+        return GR_ERR_ARG;
+    }
+    b->slot_used[slot] = 0;
+    b->slots_dirty = true;
+    return GR_OK;
+}
+
+extern "C" int gr_track_request_sweep(gr_track_bank* b, int slot) {
+    GR_REQUIRE_INIT();
+    if (!b || slot < 0 || slot >= (int)b->slot_used.size() || !b->slot_used[slot]) {
+        gr_set_error("gr_track_request_sweep: invalid slot %d", slot);
+        return GR_ERR_ARG;
+    }
+    int rc = bank_quiesce(b);
+    if (rc != GR_OK) return rc;
+    const int32_t one = 1;
+    GR_CUDA(cudaMemcpy(reinterpret_cast<char*>(b->d_state + slot) + offsetof(GrChan, h) + offsetof(GrChanHot, sweep_req), &one, sizeof(one),
+                       cudaMemcpyHostToDevice));
+    return GR_OK;
+}
+
+extern "C" int gr_track_num_active(const gr_track_bank* b) {
+    if (!b) return 0;
+    int n = 0;
+    for (int u : b->slot_used) n += u;
+    return n;
+}
+
+extern "C" int gr_track_last_launches(const gr_track_bank* b) { return b ? b->last_launches : 0; }
+
+extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int64_t rec_stride, int n_epochs,
+                                    int64_t smp_time, gr_epoch_out* d_out, void* stream) {
+    GR_REQUIRE_INIT();
+    if (!b || !d_samples || !d_out || n_epochs < 1 || rec_stride < 0) {
+        gr_set_error("gr_track_process_dev: invalid argument");
+        return GR_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (b->slots_dirty) {
+        b->active.clear();
+        for (size_t i = 0; i < b->slot_used.size(); ++i)
+            if (b->slot_used[i]) b->active.push_back((int)i);
+        if (!b->active.empty()) {
+            GR_CUDA(cudaStreamSynchronize(b->last_stream));
+            GR_CUDA(cudaMemcpy(b->d_slots, b->active.data(), b->active.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
+        b->slots_dirty = false;
+    }
+    b->last_launches = 0;
+    if (b->active.empty()) return GR_OK;
+    TrackArgs a;
+    a.samples = d_samples;
+    a.rec_stride = rec_stride;
+    a.smp_time = smp_time;
+    a.n_epochs = n_epochs;
+    a.n_active = (int)b->active.size();
+    a.slots = b->d_slots;
+    a.state = b->d_state;
+    a.out = d_out;
+    a.cfg = b->cfg;
+    a.tab = gr_lib()->tab;
+    if (b->cfg.in_format == GR_IN_U8IQ)
+        track_kernel<GR_IN_U8IQ><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);
+    else
+        track_kernel<GR_IN_CF32><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);
+    GR_CUDA(cudaGetLastError());
+    b->last_stream = s;
+    b->last_launches = 1;
+    return GR_OK;
+}
+
+extern "C" int gr_track_process_host(gr_track_bank* b, const void* h_samples, int64_t rec_stride, int nrec,
+                                     int n_epochs, int64_t smp_time, gr_epoch_out* h_out) {
+    GR_REQUIRE_INIT();
+    if (!b || !h_samples || !h_out || n_epochs < 1 || nrec < 1) {
+        gr_set_error("gr_track_process_host: invalid argument");
+        return GR_ERR_ARG;
+    }
+    GR_CUDA(cudaSetDevice(gr_lib()->device));
+    const size_t bps = b->cfg.in_format == GR_IN_U8IQ ? 2 : 8;
+    const size_t span = (size_t)n_epochs * b->cfg.n_cyc * GR_N;
+    if (nrec > 1 && (size_t)rec_stride < span) { gr_set_error("gr_track_process_host: rec_stride too short"); return GR_ERR_ARG; }
+    const size_t nsamp = (size_t)(nrec - 1) * (size_t)rec_stride + span;
+    const int nact = gr_track_num_active(b);
+    const size_t in_bytes = nsamp * bps, out_bytes = (size_t)n_epochs * nact * sizeof(gr_epoch_out);
+    if (nact == 0) return GR_OK;
+    if (in_bytes > b->in_bytes) {
+        if (b->d_in) cudaFree(b->d_in);
+        b->d_in = nullptr; b->in_bytes = 0;
+        GR_CUDA(cudaMalloc(&b->d_in, in_bytes));
+        b->in_bytes = in_bytes;
+    }
+    if (out_bytes > b->out_bytes) {
+        if (b->d_out) cudaFree(b->d_out);
+        b->d_out = nullptr; b->out_bytes = 0;
+        GR_CUDA(cudaMalloc((void**)&b->d_out, out_bytes));
+        b->out_bytes = out_bytes;
+    }
+    GR_CUDA(cudaMemcpyAsync(b->d_in, h_samples, in_bytes, cudaMemcpyHostToDevice, b->stream));
+    int rc = gr_track_process_dev(b, b->d_in, rec_stride, n_epochs, smp_time, b->d_out, (void*)b->stream);
+    if (rc != GR_OK) return rc;
+    GR_CUDA(cudaMemcpyAsync(h_out, b->d_out, out_bytes, cudaMemcpyDeviceToHost, b->stream));
+    GR_CUDA(cudaStreamSynchronize(b->stream));
+    return GR_OK;
+}

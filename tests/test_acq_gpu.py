@@ -1,0 +1,160 @@
+"""Acquisition parity on the B200: the fused CUDA kernel (through the C ABI) against the
+oracle and the golden vectors recorded from the reference.
+
+Tolerances (BASELINE.json north_star): argmax lag / Doppler bin / detected PRN set
+bit-exact; correlation magnitudes and z within 1e-4 relative."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import gps_oracle as orc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def test_fft2048_matches_numpy(gpu):
+    from gps_sdr_receiver_b200 import _capi
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((5, 2048)) + 1j * rng.standard_normal((5, 2048))).astype(np.complex64)
+    x[0] = 0
+    x[0, 1] = 1                      # single tone: exact twiddle check
+    y = np.empty_like(x)
+    _capi.check(_capi.lib().gr_debug_fft2048(x.ctypes.data, y.ctypes.data, 5, 0))
+    ref = np.fft.fft(x.astype(np.complex128), axis=1)
+    assert np.abs(y - ref).max() < 2e-6 * np.abs(ref).max()
+    _capi.check(_capi.lib().gr_debug_fft2048(x.ctypes.data, y.ctypes.data, 5, 1))
+    ref = np.fft.ifft(x.astype(np.complex128), axis=1) * 2048
+    assert np.abs(y - ref).max() < 2e-6 * np.abs(ref).max()
+
+
+def _check_cells(cells, ref, rtol=RTOL, z_clear=6.0):
+    """cells: ACQ_CELL[nprn, nbins]; ref: dict of oracle arrays [nprn, nbins]."""
+    for k in ("peak", "mean", "std", "z"):
+        np.testing.assert_allclose(cells[k], ref[k], rtol=rtol, err_msg=k)
+    clear = ref["z"] > z_clear
+    assert np.array_equal(cells["mx"][clear], ref["mx"][clear])
+    # noise cells: the argmax must be the oracle's unless two lags tie within float32 resolution
+    diff = (cells["mx"] != ref["mx"])
+    assert diff.sum() <= max(1, diff.size // 200), f"{diff.sum()} argmax mismatches"
+    same = ~diff
+    for k in ("em1", "ep1", "second"):
+        np.testing.assert_allclose(cells[k][same], ref[k][same], rtol=rtol, err_msg=k)
+
+
+def test_generalised_grid_vs_oracle_fixture(gpu, scen32):
+    """tcoh=1 ms x 10 non-coherent, |.|^2 (BASELINE config 2 shape) on a 4 PRN x 5 bin grid."""
+    from gps_sdr_receiver_b200.acquisition import AcqPlan, GR_ACQ_POW
+    g = scen32.gold
+    prns = [int(p) for p in g["grid_prns"]]
+    bins = [-1000.0 + 500.0 * b for b in range(5)]
+    plan = AcqPlan(prns, bins, 1, 10, GR_ACQ_POW)
+    cells = plan.run(scen32.raw[:2 * 10 * 2048])[0]
+    ref = {k: g[f"grid_{k}"] for k in ("mx", "peak", "mean", "std", "z", "em1", "ep1", "second")}
+    _check_cells(cells, ref)
+    assert plan.launches() == 1
+
+
+def test_reference_mode_grid_vs_reference_sweep(gpu, scen32):
+    """4 ms coherent, |.|, 31 PRN x 10 bins: z and argmax of the reference's own
+    demodDoppler/fft/ifft/findCodePhase chain (golden sweep_zgrid / sweep_mxgrid)."""
+    from gps_sdr_receiver_b200.acquisition import AcqPlan, GR_ACQ_ABS, GR_IN_CF32
+    g = scen32.gold
+    prns = list(range(2, 33))
+    bins = [-5000.0 + 200.0 * b for b in range(10)]
+    for fmt_cf32 in (False, True):
+        if fmt_cf32:
+            plan = AcqPlan(prns, bins, 4, 1, GR_ACQ_ABS, in_format=GR_IN_CF32)
+            cells = plan.run(orc.raw_to_complex(scen32.block(0))[:4 * 2048])[0]
+        else:
+            plan = AcqPlan(prns, bins, 4, 1, GR_ACQ_ABS)
+            cells = plan.run(scen32.block(0)[:2 * 4 * 2048])[0]
+        np.testing.assert_allclose(cells["z"], g["sweep_zgrid"], rtol=RTOL)
+        clear = g["sweep_zgrid"] > 6
+        assert np.array_equal(cells["mx"][clear], g["sweep_mxgrid"][clear])
+        assert (cells["mx"] != g["sweep_mxgrid"]).sum() <= 2
+
+
+@pytest.mark.parametrize("which", ["scen32", "scen8"])
+def test_sweepAllSats_drop_in(gpu, which, request):
+    """gpsrecv.sweepAllSats replacement over the 5 streams of a cold start: same
+    (z, prn, freq, delay) tuples in the same order, same carried frequency / ready flag."""
+    from gps_sdr_receiver_b200 import glob
+    from gps_sdr_receiver_b200.acquisition import sweepAllSats
+    scen = request.getfixturevalue(which)
+    glob.set_n_cyc(scen.n_cyc)
+    try:
+        g = scen.gold
+        for as_bytes in (True, False):
+            freq, lst, found, log = glob.MIN_FREQ, list(range(2, 33)), [], []
+            e, ready = 0, False
+            while not ready:
+                data = scen.block(e) if as_bytes else orc.raw_to_complex(scen.block(e))
+                ready, freq, found = sweepAllSats(data, freq, lst, found, itSweep=glob.IT_SWEEP_ALL)
+                log.append((e, ready, freq, len(found)))
+                e += 1
+            assert e == int(g["sweep_streams"])
+            assert np.array_equal(np.array(log, dtype=np.float64), g["sweep_log"])
+            got = np.array([(z, p, f, d) for z, p, f, d in found], dtype=np.float64)
+            ref = g["sweep_found"]
+            assert np.array_equal(got[:, 1:], ref[:, 1:]), (got, ref)          # prn, Doppler bin, delay: bit-exact
+            np.testing.assert_allclose(got[:, 0], ref[:, 0], rtol=RTOL)          # z
+            assert sorted(lst) == sorted(set(range(2, 33)) - set(int(p) for p in ref[:, 1]))
+    finally:
+        glob.set_n_cyc(32)
+
+
+def test_full_size_cold_start_grid_properties(gpu):
+    """BASELINE config 2 at full size (32 PRN x 41 bins x 2048, 1 ms x 10): every injected
+    satellite is found in the right Doppler bin at the right lag, absent PRNs stay below
+    threshold, batched recordings equal single runs bit for bit, device == host entry point."""
+    import torch
+    from gps_sdr_receiver_b200 import synth
+    from gps_sdr_receiver_b200.acquisition import AcqPlan, GR_ACQ_POW
+    sats = [synth.Sat(prn=3, doppler=-7250.0, delay=100.0, amp=0.09), synth.Sat(prn=11, doppler=1480.0, delay=1999.0, amp=0.09),
+            synth.Sat(prn=22, doppler=9020.0, delay=0.0, amp=0.09), synth.Sat(prn=32, doppler=-10.0, delay=2047.0, amp=0.09),
+            synth.Sat(prn=1, doppler=4510.0, delay=1023.0, amp=0.09)]
+    recs = [synth.make_iq(sats, 10, seed=s) for s in (1, 2, 3)]
+    raw = np.concatenate(recs)
+    prns = list(range(1, 33))
+    bins = [-10000.0 + 500.0 * b for b in range(41)]
+    plan = AcqPlan(prns, bins, 1, 10, GR_ACQ_POW)
+    assert plan.cells_per_recording == 2686976
+    cells = plan.run(raw, nrec=3)
+    for r in range(3):
+        single = plan.run(recs[r])[0]
+        assert cells[r].tobytes() == single.tobytes()
+    d = plan.run_dev(torch.from_numpy(raw).cuda(), nrec=3)
+    torch.cuda.synchronize()
+    assert AcqPlan.cells_from_tensor(d).tobytes() == cells.tobytes()
+    c = cells[0]
+    best = c["z"].argmax(axis=1)
+    for s in sats:
+        b = int(best[s.prn - 1])
+        assert abs(bins[b] - s.doppler) <= 250.0, (s.prn, bins[b])
+        assert int(c["mx"][s.prn - 1, b]) == int(round(s.delay)) % 2048
+        assert c["z"][s.prn - 1, b] > 12 and c["peak"][s.prn - 1, b] > 1.5 * c["second"][s.prn - 1, b]
+    absent = [p for p in prns if p not in [s.prn for s in sats]]
+    assert c["z"][[p - 1 for p in absent]].max() < 7.0
+    # spot-check a slice of the full grid against the oracle
+    ref = orc.acq_grid(orc.raw_to_complex(recs[0]), [3, 17], -8000.0, 500.0, 4, 1, 10, orc.ACQ_MODE_POW)
+    sub = c[[2, 16]][:, 4:8]
+    _check_cells(sub, ref)
+
+
+def test_ragged_and_invalid_inputs(gpu):
+    from gps_sdr_receiver_b200 import _capi
+    from gps_sdr_receiver_b200.acquisition import AcqPlan
+    plan = AcqPlan([5, 9, 13], [0.0], 2, 3)          # 3 PRNs: not a multiple of the PRN group size
+    raw = np.full(2 * 6 * 2048, 127, dtype=np.uint8)
+    cells = plan.run(raw)[0]
+    assert cells.shape == (3, 1) and np.isfinite(cells["peak"]).all()
+    with pytest.raises(ValueError):
+        plan.run(raw[:-2])                             # too short
+    with pytest.raises(TypeError):
+        plan.run(raw.astype(np.int16))
+    with pytest.raises(_capi.GrError):
+        AcqPlan([0], [0.0], 1)                         # PRN out of range
+    with pytest.raises(_capi.GrError):
+        AcqPlan([1], [], 1)                            # empty grid

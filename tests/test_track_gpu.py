@@ -1,0 +1,191 @@
+"""Tracking parity on the B200: the batched tracker kernel (through the C ABI) against
+the trajectories recorded from the reference's SatStream.process and against the oracle.
+
+Tolerances (BASELINE.json north_star): DELAY / lock / sweep decisions bit-exact,
+correlation magnitudes, prompts, code phase and carrier phase/frequency within 1e-4
+relative (code phase: 1e-4 relative of its value, i.e. well below the 7e-4 sample = 0.1 m bound)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import gps_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+COL = {n: i for i, n in enumerate(["sweep", "codePhase", "corrQ", "corrL", "FREQ", "PHASE", "DELAY", "MAX_CORR",
+                                   "AMPLITUDE", "STD_DEV", "MS_TIME", "LOCKED", "report", "n_prev", "epoch",
+                                   "smpTime", "forced", "SWP", "tracked"])}
+
+
+def _circ(a, b):
+    d = (a - b + np.pi) % (2 * np.pi) - np.pi
+    return np.abs(d)
+
+
+def _compare_channel(rows_g, recs, prompts_g, plen_g, edges_g, edges_got, tag):
+    g = lambda name: rows_g[:, COL[name]]
+    for name, field in (("sweep", "sweep"), ("DELAY", "delay"), ("LOCKED", "locked"), ("MS_TIME", "ms_time"),
+                        ("report", "report"), ("n_prev", "n_prev"), ("tracked", "tracked")):
+        assert np.array_equal(recs[field].astype(np.float64), g(name)), (tag, name, np.nonzero(recs[field] != g(name))[0][:5])
+    assert np.array_equal(recs["corr_q"], g("corrQ")) and np.array_equal(recs["corr_l"], g("corrL")), tag
+    has_cp = g("codePhase") >= 0
+    assert np.array_equal(recs["code_phase"] >= 0, has_cp), tag
+    assert np.abs(recs["code_phase"][has_cp] - g("codePhase")[has_cp]).max() < 2e-4, tag      # samples (0.03 m)
+    np.testing.assert_allclose(recs["max_corr"], g("MAX_CORR"), rtol=1e-4, err_msg=tag)
+    np.testing.assert_allclose(recs["freq"], g("FREQ"), rtol=1e-4, atol=2e-3, err_msg=tag)
+    assert _circ(recs["phase"], g("PHASE")).max() < 1e-3, tag
+    tr = g("tracked") > 0
+    np.testing.assert_allclose(recs["amplitude"][tr], g("AMPLITUDE")[tr], rtol=2e-4, err_msg=tag)
+    np.testing.assert_allclose(recs["std_dev"][tr], g("STD_DEV")[tr], rtol=2e-4, err_msg=tag)
+    rep = g("report") > 0
+    assert np.array_equal(recs["rep_sweep"][rep].astype(np.float64), g("SWP")[rep]), tag
+    assert np.array_equal(recs["n_prompt"][tr], plen_g[tr]), tag
+    for r in np.nonzero(tr)[0]:
+        n = int(plen_g[r])
+        got = np.ascontiguousarray(recs["prompt"][r][:2 * n]).view(np.complex64)
+        ref = prompts_g[r][:n]
+        assert np.abs(got - ref).max() < 1e-4 * np.abs(ref).max() + 1e-7, (tag, r)
+    assert np.array_equal(np.array(edges_got, dtype=np.int64).reshape(-1, 3), edges_g), tag
+
+
+@pytest.mark.parametrize("which,fmt", [("scen32", "u8"), ("scen32", "cf32"), ("scen8", "u8")])
+def test_bank_trajectories_match_reference(gpu, which, fmt, request):
+    """All 6 channels in one bank, multi-epoch launches, stream gap and forced sweep as in
+    oracle/make_golden.py; compared row by row with gpslib.SatStream's recorded state."""
+    from gps_sdr_receiver_b200.tracking import TrackBank, new_edges
+    from gps_sdr_receiver_b200._capi import GR_IN_CF32, GR_IN_U8IQ
+    scen = request.getfixturevalue(which)
+    g = scen.gold
+    n_cyc, ngps = scen.n_cyc, scen.ngps
+    start_e, gap_at = int(g["start_epoch"]), int(g["gap_at"])
+    chans = g["chan_init"]
+    bank = TrackBank(n_cyc, 8, GR_IN_U8IQ if fmt == "u8" else GR_IN_CF32)
+    slots = [bank.add(int(p), float(f), int(d)) for p, f, d in chans]
+    assert slots == list(range(6)) and bank.num_active == 6
+    forced = {ci: int(g[f"ch{ci}_rows"][g[f"ch{ci}_rows"][:, COL["forced"]] > 0][0, COL["epoch"]])
+              for ci in range(6) if (g[f"ch{ci}_rows"][:, COL["forced"]] > 0).any()}
+    cuts = sorted(set([start_e, gap_at, gap_at + 1, scen.n_epochs] + list(forced.values())))
+    out = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if a == gap_at:
+            continue                                    # this stream never reaches the tracker
+        for ci, ep in forced.items():
+            if ep == a:
+                bank.request_sweep(slots[ci])
+        raw = scen.raw[a * 2 * ngps:b * 2 * ngps]
+        data = raw if fmt == "u8" else orc.raw_to_complex(raw)
+        out.append(bank.process(data, (a + 1) * ngps, b - a))
+        assert bank.launches() == 1
+    recs = np.concatenate(out, axis=0)
+    for ci in range(6):
+        rows_g = g[f"ch{ci}_rows"]
+        assert len(recs) == len(rows_g)
+        edges = [(r, ms, st) for r in range(len(recs)) for ms, st in new_edges(recs[r, ci])]
+        _compare_channel(rows_g, recs[:, ci], g[f"ch{ci}_prompt"], g[f"ch{ci}_prompt_len"], g[f"ch{ci}_edges"], edges,
+                         f"{which}/{fmt}/ch{ci}")
+        assert (recs[:, ci]["prn"] == int(chans[ci][0])).all()
+    bank.close()
+
+
+def test_correlation_values_match_reference(gpu, scen32):
+    """corr[mx-1], corr[mx], corr[mx+1], mean and std of the 2048-lag correlation (cacodeCorr)
+    at the two epochs whose full vectors are in the fixture."""
+    from gps_sdr_receiver_b200.tracking import TrackBank
+    g = scen32.gold
+    start_e = int(g["start_epoch"])
+    bank = TrackBank(32, 8)
+    for p, f, d in g["chan_init"]:
+        bank.add(int(p), float(f), int(d))
+    recs = bank.process(scen32.raw[start_e * 2 * scen32.ngps:(start_e + 6) * 2 * scen32.ngps], (start_e + 1) * scen32.ngps, 6)
+    for ci in range(6):
+        for e in (0, 5):
+            c = g[f"ch{ci}_corr_e{e}"]
+            mx = int(np.argmax(c))
+            r = recs[e, ci]
+            assert r["corr_delay"] == mx
+            ref3 = np.array([c[(mx - 1) % 2048], c[mx], c[(mx + 1) % 2048]])
+            np.testing.assert_allclose(r["corr3"], ref3, rtol=1e-4)
+            np.testing.assert_allclose([r["corr_mean"], r["corr_std"]], [c.mean(), c.std()], rtol=1e-4)
+
+
+def test_satstream_drop_in_matches_oracle(gpu, scen32):
+    """The gpslib.SatStream-shaped wrapper, fed complex64 like gpsrecv does, against the
+    oracle channel run side by side (state attributes, return tuple, EDGES list, report dict)."""
+    from gps_sdr_receiver_b200 import glob
+    from gps_sdr_receiver_b200.tracking import SatStream
+    glob.set_n_cyc(32)
+    g = scen32.gold
+    start_e = int(g["start_epoch"])
+    prn, f0, dl0 = g["chan_init"][1]
+    ch = SatStream(int(prn), float(f0), delay=int(dl0), itSweep=glob.IT_SWEEP, corrMin=glob.CORR_MIN,
+                   corrAvg=glob.CORR_AVG, sweepCorrAvg=glob.SWEEP_CORR_AVG)
+    och = orc.Channel(int(prn), float(f0), delay=int(dl0), n_cyc=32)
+    assert ch.SAT_NO == int(prn)
+    smp = np.int64(start_e) * scen32.ngps
+    reports = 0
+    for ep in range(start_e, start_e + 40):
+        smp = smp + scen32.ngps
+        data = orc.raw_to_complex(scen32.block(ep))
+        sw, frames, cp, (q, l) = ch.process(data, smp)
+        sw_o, rep_o, cp_o, (q_o, l_o) = och.process(data, smp)
+        assert sw == sw_o and (len(frames) > 0) == rep_o and q == q_o and l == l_o
+        assert abs(cp - cp_o) < 2e-4
+        assert ch.DELAY == och.delay and ch.PHASE_LOCKED == och.locked and ch.MS_TIME == och.ms_time
+        assert abs(float(ch.FREQ) - float(och.freq)) < 1e-4 * abs(float(och.freq)) + 2e-3
+        assert len(ch.EDGES) == len(och.edges) and ch.EDGES[0] == och.edges[0]
+        assert ch.EDGES[1:] == och.edges[1:]
+        if frames:
+            reports += 1
+            assert set(frames[0]) >= {"SAT", "AMP", "CRM", "FRQ", "SWP"}
+            assert frames[0]["SAT"] == int(prn)
+    assert reports >= 1
+    ch.close()
+
+
+def test_many_recordings_in_one_launch(gpu, scen8):
+    """Channels of several recordings in one bank (BASELINE config 5 shape): every recording
+    is tracked exactly as if it were alone."""
+    from gps_sdr_receiver_b200.tracking import TrackBank
+    g = scen8.gold
+    start_e = int(g["start_epoch"])
+    ngps = scen8.ngps
+    n_ep = 24
+    span = n_ep * ngps
+    one = scen8.raw[start_e * 2 * ngps:(start_e + n_ep) * 2 * ngps]
+    shifted = scen8.raw[(start_e + 3) * 2 * ngps:(start_e + 3 + n_ep) * 2 * ngps]
+    both = np.concatenate([one, shifted])
+    solo0 = TrackBank(8, 8)
+    solo1 = TrackBank(8, 8)
+    duo = TrackBank(8, 16)
+    for p, f, d in g["chan_init"][:3]:
+        solo0.add(int(p), float(f), int(d))
+        solo1.add(int(p), float(f), int(d))
+    for rec in (0, 1):
+        for p, f, d in g["chan_init"][:3]:
+            duo.add(int(p), float(f), int(d), rec=rec)
+    r0 = solo0.process(one, (start_e + 1) * ngps, n_ep)
+    r1 = solo1.process(shifted, (start_e + 1) * ngps, n_ep)
+    rd = duo.process(both, (start_e + 1) * ngps, n_ep, nrec=2, rec_stride=span)
+    assert rd[:, :3].tobytes() == r0.tobytes()
+    assert rd[:, 3:].tobytes() == r1.tobytes()
+
+
+def test_bank_argument_errors(gpu):
+    from gps_sdr_receiver_b200 import _capi
+    from gps_sdr_receiver_b200.tracking import TrackBank
+    with pytest.raises(_capi.GrError):
+        TrackBank(12, 4)                      # N_CYC must divide 1024 and be >= 8
+    bank = TrackBank(8, 2)
+    bank.add(5, 100.0, 3)
+    bank.add(6, 100.0, 3)
+    with pytest.raises(_capi.GrError):
+        bank.add(7, 0.0, 0)                   # bank full
+    with pytest.raises(_capi.GrError):
+        bank.remove(5)
+    bank.remove(0)
+    assert bank.num_active == 1
+    with pytest.raises(ValueError):
+        bank.process(np.zeros(100, dtype=np.uint8), 8 * 2048, 1)
+    empty = TrackBank(8, 2)
+    assert empty.process(np.zeros(2 * 8 * 2048, dtype=np.uint8), 8 * 2048, 1).shape == (1, 0)
