@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpsb200.so")
-SOURCES = ["gr_tables.cu", "gr_acq.cu", "gr_track.cu"]
+SOURCES = ["gr_tables.cu", "gr_acq.cu", "gr_track.cu", "gr_synth.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
 

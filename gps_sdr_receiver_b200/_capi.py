@@ -33,6 +33,15 @@ EPOCH_OUT = np.dtype([
 ], align=True)
 
 
+ACQ_BEST = np.dtype([("prn", "<i4"), ("bin", "<i4"), ("cell", ACQ_CELL)])
+assert ACQ_BEST.itemsize == 40
+
+
+class SynthSat(C.Structure):
+    _fields_ = [("prn", C.c_int32), ("bit_offset_ms", C.c_int32), ("bit_seed", C.c_uint32), ("amp", C.c_float),
+                ("doppler", C.c_double), ("doppler_rate", C.c_double), ("delay", C.c_double), ("phi0", C.c_double)]
+
+
 class TrackCfg(C.Structure):
     _fields_ = [("n_cyc", C.c_int32), ("corr_avg", C.c_int32), ("sweep_corr_avg", C.c_int32),
                 ("it_sweep", C.c_int32), ("corr_min", C.c_float), ("min_freq", C.c_float),
@@ -61,6 +70,10 @@ SIGNATURES = {
     "gr_acq_run_dev": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P]),
     "gr_acq_run_host": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P]),
     "gr_acq_last_launches": (C.c_int, [_P]),
+    "gr_acq_search_dev": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P]),
+    "gr_acq_search_host": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P]),
+    "gr_synth_iq_dev": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, C.c_float, C.c_uint64, _P]),
+    "gr_debug_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "gr_track_default_cfg": (C.c_int, [C.POINTER(TrackCfg)]),
     "gr_track_bank_create": (C.c_int, [C.POINTER(TrackCfg), C.POINTER(_P)]),
     "gr_track_bank_destroy": (C.c_int, [_P]),

@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi, glob
-from ._capi import ACQ_CELL, GR_ACQ_ABS, GR_ACQ_POW, GR_IN_CF32, GR_IN_U8IQ
+from ._capi import ACQ_BEST, ACQ_CELL, GR_ACQ_ABS, GR_ACQ_POW, GR_IN_CF32, GR_IN_U8IQ
 
 
 def _is_torch(x) -> bool:
@@ -91,6 +91,37 @@ class AcqPlan:
 
     def launches(self) -> int:
         return _capi.lib().gr_acq_last_launches(self._h)
+
+    # ---- the search proper: one (PRN, Doppler bin, code phase, metric) tuple per recording and PRN ----
+    def search(self, samples, nrec: int = 1, rec_stride: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        """Host buffers in, ACQ_BEST[nrec, nprn] out (H2D + both kernels + D2H inside the call).
+        `samples` may be a pinned numpy view; no allocation when `out` is given."""
+        rec_stride = self.rec_samples if rec_stride is None else int(rec_stride)
+        a = samples if isinstance(samples, np.ndarray) and samples.flags.c_contiguous else np.ascontiguousarray(samples)
+        want = np.uint8 if self.in_format == GR_IN_U8IQ else np.complex64
+        if a.dtype != want:
+            raise TypeError(f"plan expects {np.dtype(want)} samples, got {a.dtype}")
+        self._check(a.size, nrec, rec_stride)
+        if out is None:
+            out = np.empty((nrec, len(self.prns)), dtype=ACQ_BEST)
+        _capi.check(_capi.lib().gr_acq_search_host(self._h, a.ctypes.data, nrec, rec_stride, out.ctypes.data))
+        return out
+
+    def search_dev(self, d_samples, nrec: int = 1, rec_stride: int | None = None, out=None, stream=None):
+        """Device tensor in, uint8 tensor [nrec, nprn, 40] (ACQ_BEST) out, asynchronous."""
+        import torch
+        rec_stride = self.rec_samples if rec_stride is None else int(rec_stride)
+        self._check(d_samples.numel(), nrec, rec_stride)
+        if out is None:
+            out = torch.empty((nrec, len(self.prns), ACQ_BEST.itemsize), dtype=torch.uint8, device=d_samples.device)
+        s = torch.cuda.current_stream(d_samples.device).cuda_stream if stream is None else stream
+        _capi.check(_capi.lib().gr_acq_search_dev(self._h, d_samples.data_ptr(), nrec, rec_stride, out.data_ptr(), s))
+        return out
+
+    @staticmethod
+    def best_from_tensor(t) -> np.ndarray:
+        a = t.cpu().numpy()
+        return a.view(ACQ_BEST).reshape(a.shape[:-1])
 
 
 # ---- gpsrecv-compatible functions ----------------------------------------------------

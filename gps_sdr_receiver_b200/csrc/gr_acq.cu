@@ -28,6 +28,8 @@ struct gr_acq_plan {
     // staging for the host entry point
     void* d_in;  size_t in_bytes;
     gr_acq_cell* d_out; size_t out_bytes;
+    gr_acq_cell* d_cells; size_t cells_bytes;     // scratch grid of gr_acq_search_*
+    gr_acq_best* d_best; size_t best_bytes;
     cudaStream_t stream;
     int last_launches;
 };
@@ -266,6 +268,7 @@ extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* b
     gr_acq_plan* p = new gr_acq_plan();
     p->nprn = nprn; p->nbins = nbins; p->tcoh = tcoh_ms; p->nnoncoh = nnoncoh; p->mode = mode; p->in_format = in_format;
     p->d_in = nullptr; p->in_bytes = 0; p->d_out = nullptr; p->out_bytes = 0; p->last_launches = 0;
+    p->d_cells = nullptr; p->cells_bytes = 0; p->d_best = nullptr; p->best_bytes = 0;
     std::vector<float> w(nbins);
     for (int b = 0; b < nbins; ++b) w[b] = (float)(2.0 * 3.141592653589793 * bin_hz[b]);   // 2*np.pi*freq, then weak -> float32
     GR_CUDA(cudaSetDevice(gr_lib()->device));
@@ -284,6 +287,8 @@ extern "C" int gr_acq_plan_destroy(gr_acq_plan* p) {
     cudaFree(p->d_w32);
     if (p->d_in) cudaFree(p->d_in);
     if (p->d_out) cudaFree(p->d_out);
+    if (p->d_cells) cudaFree(p->d_cells);
+    if (p->d_best) cudaFree(p->d_best);
     cudaStreamDestroy(p->stream);
     delete p;
     return GR_OK;
@@ -351,6 +356,114 @@ extern "C" int gr_acq_run_host(gr_acq_plan* p, const void* h_samples, int nrec, 
     if (rc != GR_OK) return rc;
     GR_CUDA(cudaMemcpyAsync(h_out, p->d_out, out_bytes, cudaMemcpyDeviceToHost, p->stream));
     GR_CUDA(cudaStreamSynchronize(p->stream));
+    return GR_OK;
+}
+
+// ---- best Doppler bin per (recording, PRN): the tuples that leave the device ------------------
+__global__ void acq_best_kernel(const gr_acq_cell* __restrict__ cells, const int32_t* __restrict__ prns, int nrec,
+                                int nprn, int nbins, gr_acq_best* __restrict__ best) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrec * nprn) return;
+    const gr_acq_cell* row = cells + (size_t)i * nbins;
+    int bb = 0;
+    float bz = row[0].z;
+    for (int b = 1; b < nbins; ++b) {
+        const float z = row[b].z;
+        if (z > bz) { bz = z; bb = b; }
+    }
+    gr_acq_best o;
+    o.prn = prns[i % nprn];
+    o.bin = bb;
+    o.cell = row[bb];
+    best[i] = o;
+}
+
+static int grow(void** ptr, size_t* have, size_t need) {
+    if (need <= *have) return GR_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *have = 0;
+    GR_CUDA(cudaMalloc(ptr, need));
+    *have = need;
+    return GR_OK;
+}
+
+extern "C" int gr_acq_search_dev(gr_acq_plan* p, const void* d_samples, int nrec, int64_t rec_stride,
+                                 gr_acq_best* d_best, void* stream) {
+    GR_REQUIRE_INIT();
+    if (!p || !d_samples || !d_best || nrec < 1) { gr_set_error("gr_acq_search_dev: invalid argument"); return GR_ERR_ARG; }
+    int rc = grow((void**)&p->d_cells, &p->cells_bytes, (size_t)nrec * p->nprn * p->nbins * sizeof(gr_acq_cell));
+    if (rc != GR_OK) return rc;
+    rc = gr_acq_run_dev(p, d_samples, nrec, rec_stride, p->d_cells, stream);
+    if (rc != GR_OK) return rc;
+    const int n = nrec * p->nprn;
+    acq_best_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->d_cells, p->d_prns, nrec, p->nprn, p->nbins, d_best);
+    GR_CUDA(cudaGetLastError());
+    p->last_launches = 2;
+    return GR_OK;
+}
+
+extern "C" int gr_acq_search_host(gr_acq_plan* p, const void* h_samples, int nrec, int64_t rec_stride,
+                                  gr_acq_best* h_best) {
+    GR_REQUIRE_INIT();
+    if (!p || !h_samples || !h_best || nrec < 1) { gr_set_error("gr_acq_search_host: invalid argument"); return GR_ERR_ARG; }
+    GR_CUDA(cudaSetDevice(gr_lib()->device));
+    const size_t bps = p->in_format == GR_IN_U8IQ ? 2 : 8;
+    const size_t rec_len = (size_t)p->tcoh * p->nnoncoh * GR_N;
+    if (nrec > 1 && (size_t)rec_stride < rec_len) { gr_set_error("gr_acq_search_host: rec_stride too short"); return GR_ERR_ARG; }
+    const size_t nsamp = (size_t)(nrec - 1) * (size_t)rec_stride + rec_len;
+    const size_t in_bytes = nsamp * bps, best_bytes = (size_t)nrec * p->nprn * sizeof(gr_acq_best);
+    int rc = grow(&p->d_in, &p->in_bytes, in_bytes);
+    if (rc != GR_OK) return rc;
+    rc = grow((void**)&p->d_best, &p->best_bytes, best_bytes);
+    if (rc != GR_OK) return rc;
+    GR_CUDA(cudaMemcpyAsync(p->d_in, h_samples, in_bytes, cudaMemcpyHostToDevice, p->stream));
+    rc = gr_acq_search_dev(p, p->d_in, nrec, rec_stride, p->d_best, (void*)p->stream);
+    if (rc != GR_OK) return rc;
+    GR_CUDA(cudaMemcpyAsync(h_best, p->d_best, best_bytes, cudaMemcpyDeviceToHost, p->stream));
+    GR_CUDA(cudaStreamSynchronize(p->stream));
+    return GR_OK;
+}
+
+// ---- debug hook: FP32 FFMA peak (the acquisition roofline's denominator) -----------------------
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (float)(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    if (s == 123.456f) out[0] = s;       // never true; keeps the chains alive
+}
+
+extern "C" int gr_debug_fp32_peak(int iters, double* tflops) {
+    GR_REQUIRE_INIT();
+    if (iters < 1 || !tflops) { gr_set_error("gr_debug_fp32_peak: invalid argument"); return GR_ERR_ARG; }
+    GR_CUDA(cudaSetDevice(gr_lib()->device));
+    float* d;
+    GR_CUDA(cudaMalloc(&d, 4));
+    const int blocks = gr_lib()->num_sms * 8;
+    cudaEvent_t e0, e1;
+    GR_CUDA(cudaEventCreate(&e0));
+    GR_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        GR_CUDA(cudaEventRecord(e0));
+        fma_peak_kernel<<<blocks, 256>>>(d, iters, 0.999f, 0.001f);
+        GR_CUDA(cudaEventRecord(e1));
+        GR_CUDA(cudaEventSynchronize(e1));
+        float ms;
+        GR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    GR_CUDA(cudaGetLastError());
+    *tflops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks / ((double)best * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
     return GR_OK;
 }
 

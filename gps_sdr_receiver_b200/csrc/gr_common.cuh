@@ -27,4 +27,5 @@ struct GrTables {
     const float2* conjspec;  // [GR_MAX_PRN+1][2048] conj(fft(code)), complex64, natural order
     const float2* tw1;       // [128][16]  W_2048^(t*k)    forward (e^{-i...})
     const float2* tw2;       // [8][16]    W_128^(n3*k)    forward
+    const int8_t* chips;     // [GR_MAX_PRN+1][1024] the 1023 Gold-code chips (+1/-1), padded
 };

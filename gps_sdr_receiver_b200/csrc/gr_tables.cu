@@ -125,6 +125,12 @@ extern "C" int gr_init(int device) {
             const double a = -2.0 * PI * (double)(n3 * k) / 128.0;
             tw2[n3 * 16 + k] = make_float2((float)cos(a), (float)sin(a));
         }
+    std::vector<int8_t> chips_h((size_t)(GR_MAX_PRN + 1) * 1024, 0);
+    for (int p = 1; p <= GR_MAX_PRN; ++p) memcpy(&chips_h[(size_t)p * 1024], L->chips[p], 1023);
+    int8_t* d_chips;
+    GR_CUDA(cudaMalloc(&d_chips, chips_h.size()));
+    GR_CUDA(cudaMemcpy(d_chips, chips_h.data(), chips_h.size(), cudaMemcpyHostToDevice));
+    L->tab.chips = d_chips;
     float *d_code; float2 *d_cs, *d_tw1, *d_tw2;
     GR_CUDA(cudaMalloc(&d_code, ncode * sizeof(float)));
     GR_CUDA(cudaMalloc(&d_cs, ncode * sizeof(float2)));
@@ -164,6 +170,7 @@ extern "C" int gr_shutdown(void) {
     cudaFree((void*)L->tab.conjspec);
     cudaFree((void*)L->tab.tw1);
     cudaFree((void*)L->tab.tw2);
+    cudaFree((void*)L->tab.chips);
     L->tab = GrTables{};
     L->ready = false;
     return GR_OK;

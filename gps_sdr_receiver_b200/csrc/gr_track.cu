@@ -74,6 +74,9 @@ struct gr_track_bank {
     void* d_in;  size_t in_bytes;
     gr_epoch_out* d_out; size_t out_bytes;
     int last_launches;
+    bool pipe_ready;                 // streams/events of the host pipeline
+    cudaStream_t s_in, s_out;
+    cudaEvent_t ev_in[2], ev_run[2], ev_out[2];
 };
 
 struct TrackArgs {
@@ -436,6 +439,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
                     for (int i = 0; i < C->df_len; ++i) G->df[i] = G->df_save[i];
                 }
                 O->tracked = 0;
+                for (int k = 0; k < 2 * GR_MAX_PROMPT; ++k) O->prompt[k] = 0.f;
                 O->corr_delay = delay;
                 O->code_phase = code_phase;
                 if (report) { O->rep_sweep = C->rep_sweep; O->report_freq = C->freq; C->rep_sweep = 0; }
@@ -621,6 +625,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
                 for (int h = 0; h < 2; ++h) {
                     const int k = t + 32 * h;
                     ph[h] = 0.f; ab[h] = 0.f;
+                    if (k >= np && k < GR_MAX_PROMPT) { O->prompt[2 * k] = 0.f; O->prompt[2 * k + 1] = 0.f; }
                     if (k < np) {
                         const cf g = cf{(float)S->pr_re[k], (float)S->pr_im[k]};      // np.asarray(..., complex64)
                         O->prompt[2 * k] = g.x;
@@ -799,6 +804,7 @@ extern "C" int gr_track_bank_create(const gr_track_cfg* cfg, gr_track_bank** ban
     b->slots_dirty = true;
     b->d_in = nullptr; b->in_bytes = 0; b->d_out = nullptr; b->out_bytes = 0; b->last_launches = 0;
     b->last_stream = nullptr;
+    b->pipe_ready = false;
     GR_CUDA(cudaMalloc((void**)&b->d_state, sizeof(GrChan) * (size_t)cfg->max_channels));
     GR_CUDA(cudaMemset(b->d_state, 0, sizeof(GrChan) * (size_t)cfg->max_channels));
     GR_CUDA(cudaMalloc((void**)&b->d_slots, sizeof(int32_t) * (size_t)cfg->max_channels));
@@ -817,6 +823,11 @@ extern "C" int gr_track_bank_destroy(gr_track_bank* b) {
     if (b->d_in) cudaFree(b->d_in);
     if (b->d_out) cudaFree(b->d_out);
     cudaStreamDestroy(b->stream);
+    if (b->pipe_ready) {
+        cudaStreamDestroy(b->s_in);
+        cudaStreamDestroy(b->s_out);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(b->ev_in[i]); cudaEventDestroy(b->ev_run[i]); cudaEventDestroy(b->ev_out[i]); }
+    }
     delete b;
     return GR_OK;
 }
@@ -929,6 +940,10 @@ extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int
     return GR_OK;
 }
 
+// Host entry point: the recording(s) live in host memory (pinned for full speed).  The epochs
+// are cut into chunks; chunk c+1 is copied in on one stream while chunk c is tracked on a
+// second and chunk c-1's records are copied out on a third (double-buffered) -- the stream
+// pipeline that replaces gpsrecv's deque + worker pool (gpsrecv.py:47-104, 404-417).
 extern "C" int gr_track_process_host(gr_track_bank* b, const void* h_samples, int64_t rec_stride, int nrec,
                                      int n_epochs, int64_t smp_time, gr_epoch_out* h_out) {
     GR_REQUIRE_INIT();
@@ -938,12 +953,18 @@ extern "C" int gr_track_process_host(gr_track_bank* b, const void* h_samples, in
     }
     GR_CUDA(cudaSetDevice(gr_lib()->device));
     const size_t bps = b->cfg.in_format == GR_IN_U8IQ ? 2 : 8;
-    const size_t span = (size_t)n_epochs * b->cfg.n_cyc * GR_N;
+    const size_t ngps = (size_t)b->cfg.n_cyc * GR_N;
+    const size_t span = (size_t)n_epochs * ngps;
     if (nrec > 1 && (size_t)rec_stride < span) { gr_set_error("gr_track_process_host: rec_stride too short"); return GR_ERR_ARG; }
-    const size_t nsamp = (size_t)(nrec - 1) * (size_t)rec_stride + span;
     const int nact = gr_track_num_active(b);
-    const size_t in_bytes = nsamp * bps, out_bytes = (size_t)n_epochs * nact * sizeof(gr_epoch_out);
     if (nact == 0) return GR_OK;
+    // chunk: about 16 MiB of samples over all recordings, at least one epoch
+    size_t ce = (16u << 20) / (ngps * bps * (size_t)nrec);
+    if (ce < 1) ce = 1;
+    if (ce > (size_t)n_epochs) ce = (size_t)n_epochs;
+    const size_t chunk_samples = ce * ngps;                     // per recording
+    const size_t in_bytes = 2 * chunk_samples * bps * (size_t)nrec;
+    const size_t out_bytes = 2 * ce * (size_t)nact * sizeof(gr_epoch_out);
     if (in_bytes > b->in_bytes) {
         if (b->d_in) cudaFree(b->d_in);
         b->d_in = nullptr; b->in_bytes = 0;
@@ -956,10 +977,42 @@ extern "C" int gr_track_process_host(gr_track_bank* b, const void* h_samples, in
         GR_CUDA(cudaMalloc((void**)&b->d_out, out_bytes));
         b->out_bytes = out_bytes;
     }
-    GR_CUDA(cudaMemcpyAsync(b->d_in, h_samples, in_bytes, cudaMemcpyHostToDevice, b->stream));
-    int rc = gr_track_process_dev(b, b->d_in, rec_stride, n_epochs, smp_time, b->d_out, (void*)b->stream);
-    if (rc != GR_OK) return rc;
-    GR_CUDA(cudaMemcpyAsync(h_out, b->d_out, out_bytes, cudaMemcpyDeviceToHost, b->stream));
+    if (!b->pipe_ready) {
+        GR_CUDA(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking));
+        GR_CUDA(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            GR_CUDA(cudaEventCreateWithFlags(&b->ev_in[i], cudaEventDisableTiming));
+            GR_CUDA(cudaEventCreateWithFlags(&b->ev_run[i], cudaEventDisableTiming));
+            GR_CUDA(cudaEventCreateWithFlags(&b->ev_out[i], cudaEventDisableTiming));
+        }
+        b->pipe_ready = true;
+    }
+    const char* hin = reinterpret_cast<const char*>(h_samples);
+    int launches = 0;
+    int c = 0;
+    for (size_t e0 = 0; e0 < (size_t)n_epochs; e0 += ce, ++c) {
+        const int buf = c & 1;
+        const size_t ne = (e0 + ce <= (size_t)n_epochs) ? ce : (size_t)n_epochs - e0;
+        char* din = reinterpret_cast<char*>(b->d_in) + (size_t)buf * chunk_samples * bps * (size_t)nrec;
+        gr_epoch_out* dout = b->d_out + (size_t)buf * ce * (size_t)nact;
+        if (c >= 2) GR_CUDA(cudaStreamWaitEvent(b->s_in, b->ev_run[buf], 0));      // kernel of chunk c-2 has read this buffer
+        for (int r = 0; r < nrec; ++r)
+            GR_CUDA(cudaMemcpyAsync(din + (size_t)r * chunk_samples * bps, hin + ((size_t)r * (size_t)rec_stride + e0 * ngps) * bps,
+                                    ne * ngps * bps, cudaMemcpyHostToDevice, b->s_in));
+        GR_CUDA(cudaEventRecord(b->ev_in[buf], b->s_in));
+        GR_CUDA(cudaStreamWaitEvent(b->stream, b->ev_in[buf], 0));
+        if (c >= 2) GR_CUDA(cudaStreamWaitEvent(b->stream, b->ev_out[buf], 0));    // records of chunk c-2 have left
+        int rc = gr_track_process_dev(b, din, (int64_t)chunk_samples, (int)ne, smp_time + (int64_t)(e0 * ngps), dout, (void*)b->stream);
+        if (rc != GR_OK) return rc;
+        launches += b->last_launches;
+        GR_CUDA(cudaEventRecord(b->ev_run[buf], b->stream));
+        GR_CUDA(cudaStreamWaitEvent(b->s_out, b->ev_run[buf], 0));
+        GR_CUDA(cudaMemcpyAsync(h_out + e0 * (size_t)nact, dout, ne * (size_t)nact * sizeof(gr_epoch_out), cudaMemcpyDeviceToHost, b->s_out));
+        GR_CUDA(cudaEventRecord(b->ev_out[buf], b->s_out));
+    }
+    GR_CUDA(cudaStreamSynchronize(b->s_in));
     GR_CUDA(cudaStreamSynchronize(b->stream));
+    GR_CUDA(cudaStreamSynchronize(b->s_out));
+    b->last_launches = launches;
     return GR_OK;
 }

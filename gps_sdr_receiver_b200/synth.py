@@ -121,3 +121,23 @@ def default_constellation(nsat: int = 6, seed: int = 5) -> list[Sat]:
                         bit_offset_ms=int(rng.integers(0, 20)),
                         bit_seed=k))
     return sats
+
+
+def make_iq_dev(sats: list[Sat], n_ms: int, noise_sigma: float = 0.25, seed: int = 1, start_sample: int = 0,
+                out=None, device: int = 0, stream=None):
+    """Same signal model generated on the GPU straight into HBM (csrc/gr_synth.cu; different
+    random streams than make_iq).  Returns a torch uint8 tensor [2 * n_ms * 2048]."""
+    import ctypes as C
+    import torch
+    from . import _capi
+    _capi.init(device)
+    n = n_ms * CODE_SAMPLES
+    if out is None:
+        out = torch.empty(2 * n, dtype=torch.uint8, device=f"cuda:{device}")
+    arr = (_capi.SynthSat * max(1, len(sats)))()
+    for i, s in enumerate(sats):
+        arr[i] = _capi.SynthSat(s.prn, s.bit_offset_ms, s.bit_seed, s.amp, s.doppler, s.doppler_rate, s.delay, s.phi0)
+    st = torch.cuda.current_stream(out.device).cuda_stream if stream is None else stream
+    _capi.check(_capi.lib().gr_synth_iq_dev(out.data_ptr(), n, int(start_sample), C.addressof(arr), len(sats),
+                                            float(noise_sigma), int(seed), st))
+    return out

@@ -88,6 +88,19 @@ int gr_acq_run_host(gr_acq_plan* plan, const void* h_samples, int nrec, int64_t 
 /* kernel launches issued by the last run of this plan (for bench accounting) */
 int gr_acq_last_launches(const gr_acq_plan* plan);
 
+/* The search result proper: for every recording and PRN the Doppler bin with the largest
+ * z (first maximum), i.e. the (PRN, Doppler, code-phase, metric) tuple.  The full cell grid
+ * stays in device memory (plan-owned scratch); only nrec*nprn tuples are written. */
+typedef struct gr_acq_best {
+    int32_t prn;
+    int32_t bin;        /* index into the plan's bin_hz[]                                 */
+    gr_acq_cell cell;   /* the winning (PRN, bin) cell                                    */
+} gr_acq_best;
+int gr_acq_search_dev(gr_acq_plan* plan, const void* d_samples, int nrec, int64_t rec_stride,
+                      gr_acq_best* d_best, void* stream);
+int gr_acq_search_host(gr_acq_plan* plan, const void* h_samples, int nrec, int64_t rec_stride,
+                       gr_acq_best* h_best);
+
 /* ---- tracking: a bank of channels (replaces the multiprocessing pool) ------------- */
 typedef struct gr_track_bank gr_track_bank;
 
@@ -164,9 +177,28 @@ int gr_track_process_host(gr_track_bank* bank, const void* h_samples, int64_t re
 int gr_track_num_active(const gr_track_bank* bank);
 int gr_track_last_launches(const gr_track_bank* bank);
 
+/* ---- synthetic recordings (measurement / test infrastructure) ------------ */
+typedef struct gr_synth_sat {
+    int32_t prn;
+    int32_t bit_offset_ms;   /* first nav-bit boundary, ms since the code start nearest n=0 */
+    uint32_t bit_seed;       /* nav-bit stream                                             */
+    float amp;               /* amplitude relative to full scale 1.0                       */
+    double doppler;          /* Hz at n = 0                                                */
+    double doppler_rate;     /* Hz/s                                                       */
+    double delay;            /* code phase in samples, 0 <= delay < 2048                   */
+    double phi0;             /* carrier phase at t = 0, rad                                */
+} gr_synth_sat;
+/* uint8 I,Q bytes of `nsamples` samples starting at sample `start_sample` of a recording
+ * defined by (sats, noise_sigma, seed): reproducible in pieces.  At most 16 satellites. */
+int gr_synth_iq_dev(uint8_t* d_out, int64_t nsamples, int64_t start_sample, const gr_synth_sat* sats,
+                    int nsat, float noise_sigma, uint64_t seed, void* stream);
+
 /* ---- debug / test hooks ----------------------------------------------------------------- */
 /* forward (inverse=0) or unnormalised inverse FFT-2048 of `batch` vectors, complex64 */
 int gr_debug_fft2048(const float* h_in, float* h_out, int batch, int inverse);
+/* FP32 FFMA throughput of the device (all SMs, register-resident chains): the measured
+ * denominator of the acquisition roofline.  Returns TFLOP/s (2 flop per FFMA). */
+int gr_debug_fp32_peak(int iters, double* tflops);
 
 #ifdef __cplusplus
 }

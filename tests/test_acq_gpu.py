@@ -132,8 +132,10 @@ def test_full_size_cold_start_grid_properties(gpu):
     best = c["z"].argmax(axis=1)
     for s in sats:
         b = int(best[s.prn - 1])
-        assert abs(bins[b] - s.doppler) <= 250.0, (s.prn, bins[b])
-        assert int(c["mx"][s.prn - 1, b]) == int(round(s.delay)) % 2048
+        # 1 ms coherent: the main lobe is 2 kHz wide, so z of the two bins around the true Doppler
+        # can differ by < 1 % either way (the oracle orders them the same)
+        assert abs(bins[b] - s.doppler) <= 500.0, (s.prn, bins[b])
+        assert (int(c["mx"][s.prn - 1, b]) - int(s.delay)) % 2048 in (0, 1)      # the resampled code peaks near delay + 0.5
         assert c["z"][s.prn - 1, b] > 12 and c["peak"][s.prn - 1, b] > 1.5 * c["second"][s.prn - 1, b]
     absent = [p for p in prns if p not in [s.prn for s in sats]]
     assert c["z"][[p - 1 for p in absent]].max() < 7.0
