@@ -30,6 +30,7 @@ struct gr_acq_plan {
     gr_acq_cell* d_out; size_t out_bytes;
     gr_acq_cell* d_cells; size_t cells_bytes;     // scratch grid of gr_acq_search_*
     gr_acq_best* d_best; size_t best_bytes;
+    float2* d_spec; size_t spec_bytes;            // forward spectra of one sub-batch of recordings
     cudaStream_t stream;
     int last_launches;
 };
@@ -42,6 +43,7 @@ struct AcqArgs {
     int nprn, nbins, ngroups, tcoh, nnoncoh, mode;
     float scale;               // 1 / (tcoh * 2048)
     gr_acq_cell* out;
+    float2* spec;              // scratch: forward spectra [nrec][nbins][nnoncoh][2048]
     GrTables tab;
 };
 
@@ -122,10 +124,67 @@ __device__ __forceinline__ float block_max(float v, int t, float* sh_f) {
     return r;
 }
 
-template <int G, int IN_FMT>
-__global__ void __launch_bounds__(GR_FFT_THREADS, 2) acq_kernel(const AcqArgs a) {
+// ---- kernel 1: forward spectra ------------------------------------------------------------------
+// CTA = (recording, Doppler bin, non-coherent interval).  Wipe-off, time-domain fold of the tcoh
+// blocks, ONE forward FFT; the spectrum goes to the plan's scratch (L2 / HBM), c64 natural order.
+template <int IN_FMT>
+__global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* smem = reinterpret_cast<cf*>(smem_raw);
+    const int t = threadIdx.x;
+    int id = blockIdx.x;
+    const int k = id % a.nnoncoh; id /= a.nnoncoh;
+    const int bin = id % a.nbins;
+    const int rec = id / a.nbins;
+
+    cf tw1[16], tw2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float2 u = a.tab.tw1[t * 16 + i];
+        const float2 v = a.tab.tw2[(t & 7) * 16 + i];
+        tw1[i] = cf{u.x, u.y};
+        tw2[i] = cf{v.x, v.y};
+    }
+    const float w32 = a.w32[bin];
+    const long long rec_off = (long long)rec * a.rec_stride;
+    const void* src = (IN_FMT == GR_IN_U8IQ)
+                          ? (const void*)(reinterpret_cast<const uchar2*>(a.samples) + rec_off)
+                          : (const void*)(reinterpret_cast<const float2*>(a.samples) + rec_off);
+    cf X[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) X[j] = cf{0.f, 0.f};
+    for (int i = 0; i < a.tcoh; ++i) {
+        const long long base = (long long)(k * a.tcoh + i) * GR_N;
+        cf s[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s[j] = load_sample<IN_FMT>(src, base + t + 128 * j);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float sn, cs;
+            sincosf(nco_arg(w32, base + t + 128 * j), &sn, &cs);
+            X[j].x += s[j].x * cs + s[j].y * sn;              // s * exp(-i arg)
+            X[j].y += s[j].y * cs - s[j].x * sn;
+        }
+    }
+    fft2048<true>(X, smem, tw1, tw2, t);
+    float2* dst = a.spec + ((size_t)(rec * a.nbins + bin) * a.nnoncoh + k) * GR_N;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dst[t + 128 * j] = make_float2(X[j].x, X[j].y);
+}
+
+// ---- kernel 2: x conj(code spectrum), inverse FFT, non-coherent accumulation, cell statistics ------
+// CTA = (recording, Doppler bin, group of G PRNs), PRN groups fastest so that the CTAs sharing
+// a forward spectrum run together and hit it in L2.  The PRN loop and the interval loop are real
+// loops around ONE FFT code path (it stays in the instruction cache); the conjugate code spectrum
+// of the current PRN sits in registers across the K intervals; the next interval's spectrum is
+// prefetched into L1 while the current FFT runs.  Stage-2 twiddles come from shared memory to keep
+// the kernel at 3 CTAs / SM.
+#define GR_TW2_STRIDE 17
+template <int G>
+__global__ void __launch_bounds__(GR_FFT_THREADS, 3) acq_inv_kernel(const AcqArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf* smem = reinterpret_cast<cf*>(smem_raw);
+    cf* tw2s = smem + GR_B1_ELEMS + GR_B2_ELEMS;              // [8][17]
     __shared__ double sh_d[8];
     __shared__ float sh_f[4];
     __shared__ int sh_i[4];
@@ -136,87 +195,67 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, 2) acq_kernel(const AcqArgs a)
     const int bin = id % a.nbins;
     const int rec = id / a.nbins;
 
-    // per-thread twiddles, constant for the whole kernel
-    cf tw1[16], tw2[16];
+    cf tw1[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const float2 u = a.tab.tw1[t * 16 + k];
-        const float2 v = a.tab.tw2[(t & 7) * 16 + k];
-        tw1[k] = cf{u.x, u.y};
-        tw2[k] = cf{v.x, v.y};
+    for (int i = 0; i < 16; ++i) {
+        const float2 u = a.tab.tw1[t * 16 + i];
+        tw1[i] = cf{u.x, u.y};
     }
+    {
+        const float2 v = a.tab.tw2[t];                         // 8 x 16 entries = 128 threads
+        tw2s[(t >> 4) * GR_TW2_STRIDE + (t & 15)] = cf{v.x, v.y};
+    }
+    __syncthreads();
+    const cf* tw2 = tw2s + (t & 7) * GR_TW2_STRIDE;
 
-    const float w32 = a.w32[bin];
-    const long long rec_off = (long long)rec * a.rec_stride;
-    const void* src = (IN_FMT == GR_IN_U8IQ)
-                          ? (const void*)(reinterpret_cast<const uchar2*>(a.samples) + rec_off)
-                          : (const void*)(reinterpret_cast<const float2*>(a.samples) + rec_off);
+    const float2* spec = a.spec + (size_t)(rec * a.nbins + bin) * a.nnoncoh * GR_N + t;
+    const float sc = (a.mode == GR_ACQ_POW) ? a.scale * a.scale : a.scale;
 
-    int prn[G];
-#pragma unroll
     for (int g = 0; g < G; ++g) {
         const int pi = grp * G + g;
-        prn[g] = pi < a.nprn ? a.prns[pi] : 0;
-    }
-
-    float acc[G][16];
+        if (pi >= a.nprn) break;                               // uniform across the CTA
+        const float2* cs = a.tab.conjspec + (size_t)a.prns[pi] * GR_N + t;
+        cf c[16];
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[g][j] = 0.f;
-
-    for (int k = 0; k < a.nnoncoh; ++k) {
-        // ---- wipe-off + coherent fold of tcoh 1-ms blocks (time domain) ----
-        cf X[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) X[j] = cf{0.f, 0.f};
-        for (int i = 0; i < a.tcoh; ++i) {
-            const long long base = (long long)(k * a.tcoh + i) * GR_N;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const long long n = base + t + 128 * j;
-                const cf s = load_sample<IN_FMT>(src, n);
-                float sn, cs;
-                sincosf(nco_arg(w32, n), &sn, &cs);
-                // s * exp(-i arg)
-                X[j].x += s.x * cs + s.y * sn;
-                X[j].y += s.y * cs - s.x * sn;
-            }
+        for (int j = 0; j < 16; ++j) {
+            const float2 v = __ldg(cs + 128 * j);
+            c[j] = cf{v.x, v.y};
         }
-        fft2048<true>(X, smem, tw1, tw2, t);
-
-        // ---- per PRN: x conj(code spectrum), inverse FFT (swap form), accumulate ----
+        float acc[16];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            if (prn[g] == 0) continue;                       // uniform across the CTA
-            const float2* cs = a.tab.conjspec + (size_t)prn[g] * GR_N;
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        for (int k = 0; k < a.nnoncoh; ++k) {
             cf y[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float2 c = __ldg(cs + t + 128 * j);
+                const float2 v = __ldg(spec + (size_t)k * GR_N + 128 * j);
+                y[j] = cf{v.x, v.y};
+            }
+            if (k + 1 < a.nnoncoh) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(spec + (size_t)(k + 1) * GR_N + 128 * j));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
                 // Y = X * conjC ; operand of the swap-form inverse = (Im Y, Re Y)
-                y[j].x = X[j].x * c.y + X[j].y * c.x;
-                y[j].y = X[j].x * c.x - X[j].y * c.y;
+                const cf x = y[j];
+                y[j].x = x.x * c[j].y + x.y * c[j].x;
+                y[j].y = x.x * c[j].x - x.y * c[j].y;
             }
             fft2048<true>(y, smem, tw1, tw2, t);
             if (a.mode == GR_ACQ_POW) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[g][j] += y[j].x * y[j].x + y[j].y * y[j].y;
+                for (int j = 0; j < 16; ++j) acc[j] += y[j].x * y[j].x + y[j].y * y[j].y;
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[g][j] += sqrtf(y[j].x * y[j].x + y[j].y * y[j].y);
+                for (int j = 0; j < 16; ++j) acc[j] += sqrtf(y[j].x * y[j].x + y[j].y * y[j].y);
             }
         }
-    }
-
-    // ---- reduce every PRN's 2048 lags to one cell ----
-    const float sc = (a.mode == GR_ACQ_POW) ? a.scale * a.scale : a.scale;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        if (prn[g] == 0) continue;
+        // ---- reduce this PRN's 2048 lags to one cell ----
         float st[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) st[j] = acc[g][j] * sc;
+        for (int j = 0; j < 16; ++j) st[j] = acc[j] * sc;
         const BlockStat bs = block_stats(st, t, sh_d, sh_f, sh_i);
         const int mx = bs.idx;
         float sec = -1.f;
@@ -229,7 +268,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, 2) acq_kernel(const AcqArgs a)
             if (d > GR_SECOND_PEAK_GUARD) sec = fmaxf(sec, st[j]);
         }
         sec = block_max(sec, t, sh_f);
-        gr_acq_cell* cell = a.out + ((size_t)rec * a.nprn + (grp * G + g)) * a.nbins + bin;
+        gr_acq_cell* cell = a.out + ((size_t)rec * a.nprn + pi) * a.nbins + bin;
         const int lo = (mx + GR_N - 1) & (GR_N - 1), hi = (mx + 1) & (GR_N - 1);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -269,6 +308,7 @@ extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* b
     p->nprn = nprn; p->nbins = nbins; p->tcoh = tcoh_ms; p->nnoncoh = nnoncoh; p->mode = mode; p->in_format = in_format;
     p->d_in = nullptr; p->in_bytes = 0; p->d_out = nullptr; p->out_bytes = 0; p->last_launches = 0;
     p->d_cells = nullptr; p->cells_bytes = 0; p->d_best = nullptr; p->best_bytes = 0;
+    p->d_spec = nullptr; p->spec_bytes = 0;
     std::vector<float> w(nbins);
     for (int b = 0; b < nbins; ++b) w[b] = (float)(2.0 * 3.141592653589793 * bin_hz[b]);   // 2*np.pi*freq, then weak -> float32
     GR_CUDA(cudaSetDevice(gr_lib()->device));
@@ -289,12 +329,25 @@ extern "C" int gr_acq_plan_destroy(gr_acq_plan* p) {
     if (p->d_out) cudaFree(p->d_out);
     if (p->d_cells) cudaFree(p->d_cells);
     if (p->d_best) cudaFree(p->d_best);
+    if (p->d_spec) cudaFree(p->d_spec);
     cudaStreamDestroy(p->stream);
     delete p;
     return GR_OK;
 }
 
 extern "C" int gr_acq_last_launches(const gr_acq_plan* p) { return p ? p->last_launches : 0; }
+
+static int grow(void** ptr, size_t* have, size_t need) {
+    if (need <= *have) return GR_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *have = 0;
+    GR_CUDA(cudaMalloc(ptr, need));
+    *have = need;
+    return GR_OK;
+}
+
+#define GR_ACQ_SPEC_CAP (8ull << 30)     // scratch for forward spectra: at most 8 GiB per sub-batch
+#define GR_ACQ_INV_SMEM (GR_FFT_SMEM_BYTES + 8 * GR_TW2_STRIDE * 8)
 
 extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, int64_t rec_stride,
                               gr_acq_cell* d_out, void* stream) {
@@ -304,28 +357,44 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         gr_set_error("gr_acq_run_dev: rec_stride %lld shorter than one recording", (long long)rec_stride);
         return GR_ERR_ARG;
     }
-    AcqArgs a;
-    a.samples = d_samples;
-    a.rec_stride = rec_stride;
-    a.prns = p->d_prns;
-    a.w32 = p->d_w32;
-    a.nprn = p->nprn;
-    a.nbins = p->nbins;
-    a.ngroups = (p->nprn + GR_ACQ_G - 1) / GR_ACQ_G;
-    a.tcoh = p->tcoh;
-    a.nnoncoh = p->nnoncoh;
-    a.mode = p->mode;
-    a.scale = 1.0f / ((float)p->tcoh * (float)GR_N);
-    a.out = d_out;
-    a.tab = gr_lib()->tab;
-    const long long nblocks = (long long)nrec * p->nbins * a.ngroups;
-    if (nblocks > 0x7fffffffLL) { gr_set_error("gr_acq_run_dev: grid too large"); return GR_ERR_ARG; }
+    const size_t spec_per_rec = (size_t)p->nbins * p->nnoncoh * GR_N * sizeof(float2);
+    int sub = (int)(GR_ACQ_SPEC_CAP / spec_per_rec);
+    if (sub < 1) sub = 1;
+    if (sub > nrec) sub = nrec;
+    int rc = grow((void**)&p->d_spec, &p->spec_bytes, (size_t)sub * spec_per_rec);
+    if (rc != GR_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    auto kern = p->in_format == GR_IN_U8IQ ? acq_kernel<GR_ACQ_G, GR_IN_U8IQ> : acq_kernel<GR_ACQ_G, GR_IN_CF32>;
-    GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_FFT_SMEM_BYTES));
-    kern<<<(unsigned)nblocks, GR_FFT_THREADS, GR_FFT_SMEM_BYTES, s>>>(a);
-    GR_CUDA(cudaGetLastError());
-    p->last_launches = 1;
+    auto fwd = p->in_format == GR_IN_U8IQ ? acq_fwd_kernel<GR_IN_U8IQ> : acq_fwd_kernel<GR_IN_CF32>;
+    auto inv = acq_inv_kernel<GR_ACQ_G>;
+    GR_CUDA(cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_FFT_SMEM_BYTES));
+    GR_CUDA(cudaFuncSetAttribute(inv, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_ACQ_INV_SMEM));
+    const size_t bps = p->in_format == GR_IN_U8IQ ? 2 : 8;
+    p->last_launches = 0;
+    for (int r0 = 0; r0 < nrec; r0 += sub) {
+        const int nr = (r0 + sub <= nrec) ? sub : nrec - r0;
+        AcqArgs a;
+        a.samples = reinterpret_cast<const char*>(d_samples) + (size_t)r0 * (size_t)rec_stride * bps;
+        a.rec_stride = rec_stride;
+        a.prns = p->d_prns;
+        a.w32 = p->d_w32;
+        a.nprn = p->nprn;
+        a.nbins = p->nbins;
+        a.ngroups = (p->nprn + GR_ACQ_G - 1) / GR_ACQ_G;
+        a.tcoh = p->tcoh;
+        a.nnoncoh = p->nnoncoh;
+        a.mode = p->mode;
+        a.scale = 1.0f / ((float)p->tcoh * (float)GR_N);
+        a.out = d_out + (size_t)r0 * p->nprn * p->nbins;
+        a.spec = p->d_spec;
+        a.tab = gr_lib()->tab;
+        const long long nfwd = (long long)nr * p->nbins * p->nnoncoh;
+        const long long ninv = (long long)nr * p->nbins * a.ngroups;
+        if (nfwd > 0x7fffffffLL || ninv > 0x7fffffffLL) { gr_set_error("gr_acq_run_dev: grid too large"); return GR_ERR_ARG; }
+        fwd<<<(unsigned)nfwd, GR_FFT_THREADS, GR_FFT_SMEM_BYTES, s>>>(a);
+        inv<<<(unsigned)ninv, GR_FFT_THREADS, GR_ACQ_INV_SMEM, s>>>(a);
+        GR_CUDA(cudaGetLastError());
+        p->last_launches += 2;
+    }
     return GR_OK;
 }
 
@@ -378,15 +447,6 @@ __global__ void acq_best_kernel(const gr_acq_cell* __restrict__ cells, const int
     best[i] = o;
 }
 
-static int grow(void** ptr, size_t* have, size_t need) {
-    if (need <= *have) return GR_OK;
-    if (*ptr) cudaFree(*ptr);
-    *ptr = nullptr; *have = 0;
-    GR_CUDA(cudaMalloc(ptr, need));
-    *have = need;
-    return GR_OK;
-}
-
 extern "C" int gr_acq_search_dev(gr_acq_plan* p, const void* d_samples, int nrec, int64_t rec_stride,
                                  gr_acq_best* d_best, void* stream) {
     GR_REQUIRE_INIT();
@@ -398,7 +458,7 @@ extern "C" int gr_acq_search_dev(gr_acq_plan* p, const void* d_samples, int nrec
     const int n = nrec * p->nprn;
     acq_best_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->d_cells, p->d_prns, nrec, p->nprn, p->nbins, d_best);
     GR_CUDA(cudaGetLastError());
-    p->last_launches = 2;
+    p->last_launches += 1;
     return GR_OK;
 }
 

@@ -168,7 +168,6 @@ __device__ __forceinline__ void corr_and_stats(cf* F, const float2* __restrict__
         y[j].x = F[j].x * c.y + F[j].y * c.x;      // swap form of the inverse transform
         y[j].y = F[j].x * c.x - F[j].y * c.y;
     }
-    __syncthreads();                               // fftbuf is reused by the second transform
     fft2048<true>(y, fftbuf, tw1, tw2, t);
     float st[16];
     float s = 0.f, s2 = 0.f, mx = -1.f;
@@ -503,12 +502,18 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
                 const int k1 = (k0 + GR_PART_ROWS <= n_cyc + 1) ? k0 + GR_PART_ROWS : n_cyc + 1;
                 for (int k = k0; k < k1; ++k) {
                     const long long base = (long long)128 * jb + (long long)GR_N * (k - 1) + t;
+                    // rows outside the epoch (pass 0: not yet wrapped, last pass: wrapped) read a clamped
+                    // address and are zeroed with selects: no branches around the loads
+                    const int vmode = (k == 0) ? 1 : (k == n_cyc ? 2 : 0);
                     cf x[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const bool wrapped = (j + jb) >= 16;
-                        const bool valid = (k == 0) ? wrapped : (k == n_cyc ? !wrapped : true);
-                        x[j] = valid ? load_raw<IN_FMT>(src, base + 128 * j) : cf{0.f, 0.f};
+                        const bool valid = vmode == 0 || (vmode == 1 ? wrapped : !wrapped);
+                        const long long n = valid ? base + 128 * j : (long long)t;
+                        const cf v = load_raw<IN_FMT>(src, n);
+                        x[j].x = valid ? v.x : 0.f;
+                        x[j].y = valid ? v.y : 0.f;
                     }
                     cf p0 = cmul(x[0], q[0]);
                     cf acc = p0;

@@ -33,7 +33,7 @@ def _compare_channel(rows_g, recs, prompts_g, plen_g, edges_g, edges_got, tag, e
     assert np.array_equal(recs["code_phase"] >= 0, has_cp), tag
     assert np.abs(recs["code_phase"][has_cp] - g("codePhase")[has_cp]).max() < 2e-4, tag      # samples (0.03 m)
     np.testing.assert_allclose(recs["max_corr"], g("MAX_CORR"), rtol=1e-4, err_msg=tag)
-    np.testing.assert_allclose(recs["freq"], g("FREQ"), rtol=1e-4, atol=2e-3, err_msg=tag)
+    np.testing.assert_allclose(recs["freq"], g("FREQ"), rtol=1e-6, atol=1e-3, err_msg=tag)
     assert _circ(recs["phase"], g("PHASE")).max() < 1e-3, tag
     tr = g("tracked") > 0
     np.testing.assert_allclose(recs["amplitude"][tr], g("AMPLITUDE")[tr], rtol=2e-4, err_msg=tag)
@@ -43,16 +43,18 @@ def _compare_channel(rows_g, recs, prompts_g, plen_g, edges_g, edges_got, tag, e
     assert np.array_equal(recs["n_prompt"][tr], plen_g[tr]), tag
     # Prompt values.  |prompt| within 1e-4.  The complex value additionally carries the carrier
     # phase, and the reference keeps FREQ in float32: the kernel's FREQ agrees to the last bit or
-    # one ulp (2.4e-4 Hz at 3 kHz, from 1e-7-level differences in the discriminator), and one ulp
-    # rotates the last prompt of a 32-ms epoch by 2*pi*2.4e-4*0.032 = 5e-5 rad until the loop
-    # pulls it back.  Hence 4e-4 of the amplitude for the complex difference.
+    # a few ulp (1 ulp = 2.4e-4 Hz at 3 kHz; up to 7 ulp = 5.7e-7 relative right after a re-sweep,
+    # where the unlocked loop gain of 10 amplifies 1e-6-level discriminator differences), and
+    # 1.7e-3 Hz rotates the last prompt of a 32-ms epoch by 2*pi*1.7e-3*0.032 = 3.4e-4 rad until
+    # the loop pulls it back (trace: tools/diag_track.py).  Hence 1e-3 of the amplitude for the
+    # complex difference; FREQ itself is checked at 1e-6 relative below.
     for r in np.nonzero(tr)[0]:
         n = int(plen_g[r])
         got = np.ascontiguousarray(recs["prompt"][r][:2 * n]).view(np.complex64)
         ref = prompts_g[r][:n]
         scale = np.abs(ref).max()
         assert np.abs(np.abs(got) - np.abs(ref)).max() < 1e-4 * scale + 1e-7, (tag, r)
-        assert np.abs(got - ref).max() < 4e-4 * scale + 1e-7, (tag, r)
+        assert np.abs(got - ref).max() < 1e-3 * scale + 1e-7, (tag, r)
     got_e = set(map(tuple, np.array(edges_got, dtype=np.int64).reshape(-1, 3).tolist()))
     ref_e = set(map(tuple, edges_g.tolist()))
     if exact_edges:
