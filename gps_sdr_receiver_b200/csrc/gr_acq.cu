@@ -231,11 +231,9 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, 3) acq_inv_kernel(const AcqArg
                 const float2 v = __ldg(spec + (size_t)k * GR_N + 128 * j);
                 y[j] = cf{v.x, v.y};
             }
-            if (k + 1 < a.nnoncoh) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(spec + (size_t)(k + 1) * GR_N + 128 * j));
-            }
+            // one prefetch per thread covers the next spectrum: thread t touches its 128-byte line t
+            if (k + 1 < a.nnoncoh)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(spec - t + (size_t)(k + 1) * GR_N + 16 * t));
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 // Y = X * conjC ; operand of the swap-form inverse = (Im Y, Re Y)

@@ -147,13 +147,17 @@ class SatStream:
     decoder can be attached with `frame_decoder`."""
 
     def __init__(self, satNo, freq, itSweep=10, corrMin=8, corrAvg=8, sweepCorrAvg=4, delay=0,
-                 in_format: int | None = None, frame_decoder=None, device: int = 0):
+                 in_format: int | None = None, frame_decoder=None, device: int = 0, bank: TrackBank | None = None):
         self.SAT_NO = satNo
         self._args = dict(corr_avg=corrAvg, sweep_corr_avg=sweepCorrAvg, it_sweep=itSweep, corr_min=corrMin, device=device)
         self._init = (int(satNo), float(freq), int(delay))
         self._banks: dict[int, tuple[TrackBank, int]] = {}
         self._fmt = in_format
         self._bank = None
+        self._shared = bank is not None            # a slot of somebody else's bank (ChannelPool)
+        if bank is not None:
+            self._bank, self._fmt = bank, bank.in_format
+            self._slot = bank.add(*self._init)
         self._decoder = frame_decoder
         self.NO_SEC = 1024 // glob.N_CYC
         self.EDGES = [0]
@@ -248,9 +252,17 @@ class SatStream:
             self.EDGES = [last, self.EDGES[-1]]
         return frames
 
+    def absorb(self, rec, smpTime):
+        """Update the host mirror from this channel's gr_epoch_out record (batched use)."""
+        return self._absorb(rec, int(smpTime))
+
     def close(self):
         if self._bank is not None:
-            self._bank.close()
+            if self._shared:
+                if getattr(self._bank, "_h", None):
+                    self._bank.remove(self._slot)
+            else:
+                self._bank.close()
             self._bank = None
 
     def __del__(self):
