@@ -104,10 +104,11 @@ GR_HD void dft8(cf* a) {
 // ---- the three stages, split so that a host emulation can run them per "thread" ----
 
 // tw1: this thread's 16 stage-1 twiddles W_2048^(t*k1) (forward); tw2: W_128^(n3*k2)
+template <int TW1_STRIDE = 1>
 GR_HD void fft_stage1(cf* v, const cf* tw1) {
     dft16(v);
 #pragma unroll
-    for (int k = 1; k < 16; ++k) v[k] = cmul(v[k], tw1[k]);
+    for (int k = 1; k < 16; ++k) v[k] = cmul(v[k], tw1[k * TW1_STRIDE]);
 }
 GR_HD void fft_ex1_write(cf* buf1, int t, const cf* v) {
 #pragma unroll
@@ -148,11 +149,12 @@ GR_HD void fft_ex2_read_stage3(const cf* buf2, int t, cf* v) {
 #if defined(__CUDACC__)
 // Forward FFT-2048 across the 128 threads of a CTA (or of a 128-thread group
 // using its own buffers and `bar_id` as named barrier).  smem = buf1 | buf2.
-template <bool kWholeCta>
+// TW1_STRIDE > 1: stage-1 twiddles read from a shared-memory table laid out [k][thread].
+template <bool kWholeCta, int TW1_STRIDE = 1>
 __device__ __forceinline__ void fft2048(cf* v, cf* smem, const cf* tw1, const cf* tw2, int t, int bar_id = 1) {
     cf* buf1 = smem;
     cf* buf2 = smem + GR_B1_ELEMS;
-    fft_stage1(v, tw1);
+    fft_stage1<TW1_STRIDE>(v, tw1);
     fft_ex1_write(buf1, t, v);
     if (kWholeCta) __syncthreads(); else asm volatile("bar.sync %0, 128;" ::"r"(bar_id));
     fft_ex1_read(buf1, t, v);
