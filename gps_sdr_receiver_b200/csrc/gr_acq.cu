@@ -16,7 +16,6 @@
 // register-resident accumulator (16 lags per thread per PRN).  Nothing but the final
 // 32-byte cell per (PRN, bin) is written to HBM.
 #include <stdio.h>
-#include <stdlib.h>
 #include <vector>
 
 #include "gr_fft2048.cuh"
@@ -44,6 +43,7 @@ struct AcqArgs {
     const int32_t* prns;
     const float* w32;
     int nprn, nbins, ngroups, tcoh, nnoncoh, mode;
+    int nchunks, bins_per_chunk;   // forward kernel: Doppler bins per CTA
     float scale;               // 1 / (tcoh * 2048)
     gr_acq_cell* out;
     float2* spec;              // scratch: forward spectra [nrec][nbins][nnoncoh][2048]
@@ -128,17 +128,32 @@ __device__ __forceinline__ float block_max(float v, int t, float* sh_f) {
 }
 
 // ---- kernel 1: forward spectra ------------------------------------------------------------------
-// CTA = (recording, Doppler bin, non-coherent interval).  Wipe-off, time-domain fold of the tcoh
-// blocks, ONE forward FFT; the spectrum goes to the plan's scratch (L2 / HBM), c64 natural order.
-template <int IN_FMT, bool kPaired = false>
+// CTA = (recording, non-coherent interval, chunk of Doppler bins); it loops over its bins with the FFT
+// twiddles (and, for tcoh = 1, the 16 samples per thread) held in registers: wipe-off, time-domain fold of
+// the tcoh blocks, ONE forward FFT per bin; the spectrum goes to the plan's scratch in the paired layout
+// [j >> 1][t][j & 1] the inverse kernel's TMA stage expects (8 x 128-bit per thread).
+//
+// NCO: the phase argument is the reference's float32 one, arg = fl32(w32 * fl32((n+1)/fs))
+// (gpsrecv.py:32-33, 232-235); sin/cos of it come from a 2-constant Cody-Waite reduction + MUFU
+// (|err| < 5e-7 absolute, i.e. below the float32 rounding of the argument itself, 3e-5 rad at 10 kHz x 10 ms).
+__device__ __forceinline__ cf nco_fast(float arg) {            // exp(-i arg)
+    const float k = rintf(arg * 0.15915494309189535f);
+    float r = fmaf(k, -6.28125f, arg);                         // 6.28125 = 201/32: k * C1 is exact
+    r = fmaf(k, -1.9353071795864769e-3f, r);                   // 2 pi - 6.28125
+    return cf{__cosf(r), -__sinf(r)};
+}
+
+template <int IN_FMT, bool kOneBlock>
 __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* smem = reinterpret_cast<cf*>(smem_raw);
     const int t = threadIdx.x;
     int id = blockIdx.x;
-    const int k = id % a.nnoncoh; id /= a.nnoncoh;
-    const int bin = id % a.nbins;
-    const int rec = id / a.nbins;
+    const int chunk = id % a.nchunks; id /= a.nchunks;
+    const int k = id % a.nnoncoh;
+    const int rec = id / a.nnoncoh;
+    const int bin0 = chunk * a.bins_per_chunk;
+    const int bin1 = min(a.nbins, bin0 + a.bins_per_chunk);
 
     cf tw1[16], tw2[16];
 #pragma unroll
@@ -148,36 +163,38 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
         tw1[i] = cf{u.x, u.y};
         tw2[i] = cf{v.x, v.y};
     }
-    const float w32 = a.w32[bin];
     const long long rec_off = (long long)rec * a.rec_stride;
     const void* src = (IN_FMT == GR_IN_U8IQ)
                           ? (const void*)(reinterpret_cast<const uchar2*>(a.samples) + rec_off)
                           : (const void*)(reinterpret_cast<const float2*>(a.samples) + rec_off);
-    cf X[16];
+    const long long base0 = (long long)k * a.tcoh * GR_N + t;
+    cf s0[kOneBlock ? 16 : 1];
+    if (kOneBlock) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) X[j] = cf{0.f, 0.f};
-    for (int i = 0; i < a.tcoh; ++i) {
-        const long long base = (long long)(k * a.tcoh + i) * GR_N;
-        cf s[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) s[j] = load_sample<IN_FMT>(src, base + t + 128 * j);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float sn, cs;
-            sincosf(nco_arg(w32, base + t + 128 * j), &sn, &cs);
-            X[j].x += s[j].x * cs + s[j].y * sn;              // s * exp(-i arg)
-            X[j].y += s[j].y * cs - s[j].x * sn;
-        }
+        for (int j = 0; j < 16; ++j) s0[kOneBlock ? j : 0] = load_sample<IN_FMT>(src, base0 + 128 * j);
     }
-    fft2048<true>(X, smem, tw1, tw2, t);
-    float2* dst = a.spec + ((size_t)(rec * a.nbins + bin) * a.nnoncoh + k) * GR_N;
-    if (kPaired) {        // [j >> 1][t][j & 1]: the inverse kernel's thread t fetches its 16 points as 8 x 128-bit
-        float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int bin = bin0; bin < bin1; ++bin) {
+        const float w32 = a.w32[bin];
+        cf X[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) X[j] = cf{0.f, 0.f};
+        for (int i = 0; i < (kOneBlock ? 1 : a.tcoh); ++i) {
+            const long long base = base0 + (long long)i * GR_N;
+            cf s[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s[j] = kOneBlock ? s0[kOneBlock ? j : 0] : load_sample<IN_FMT>(src, base + 128 * j);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const cf e = nco_fast(nco_arg(w32, base + 128 * j));      // exp(-i arg)
+                X[j].x += s[j].x * e.x - s[j].y * e.y;
+                X[j].y += s[j].y * e.x + s[j].x * e.y;
+            }
+        }
+        fft2048<true>(X, smem, tw1, tw2, t);
+        float4* d4 = reinterpret_cast<float4*>(a.spec + ((size_t)(rec * a.nbins + bin) * a.nnoncoh + k) * GR_N);
 #pragma unroll
         for (int m = 0; m < 8; ++m) d4[m * 128 + t] = make_float4(X[2 * m].x, X[2 * m].y, X[2 * m + 1].x, X[2 * m + 1].y);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) dst[t + 128 * j] = make_float2(X[j].x, X[j].y);
+        __syncthreads();                                           // the FFT buffers are reused by the next bin
     }
 }
 
@@ -220,98 +237,17 @@ __device__ __forceinline__ void acq_cell_epilogue(const float* st, int nb, int t
 }
 
 // ---- kernel 2: x conj(code spectrum), inverse FFT, non-coherent accumulation, cell statistics ------
-// CTA = (recording, Doppler bin, group of G PRNs), PRN groups fastest so that the CTAs sharing
-// a forward spectrum run together and hit it in L2.  The PRN loop and the interval loop are real
-// loops around ONE FFT code path (it stays in the instruction cache); the conjugate code spectrum
-// of the current PRN sits in registers across the K intervals; the next interval's spectrum is
-// prefetched into L1 while the current FFT runs.  Stage-2 twiddles come from shared memory to keep
-// the kernel at 3 CTAs / SM.
-#define GR_TW2_STRIDE 17
-template <int G>
-__global__ void __launch_bounds__(GR_FFT_THREADS, 3) acq_inv_kernel(const AcqArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cf* smem = reinterpret_cast<cf*>(smem_raw);
-    cf* tw2s = smem + GR_B1_ELEMS + GR_B2_ELEMS;              // [8][17]
-    __shared__ double sh_d[8];
-    __shared__ float sh_f[4];
-    __shared__ int sh_i[4];
-
-    const int t = threadIdx.x;
-    int id = blockIdx.x;
-    const int grp = id % a.ngroups; id /= a.ngroups;
-    const int bin = id % a.nbins;
-    const int rec = id / a.nbins;
-
-    cf tw1[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float2 u = a.tab.tw1[t * 16 + i];
-        tw1[i] = cf{u.x, u.y};
-    }
-    {
-        const float2 v = a.tab.tw2[t];                         // 8 x 16 entries = 128 threads
-        tw2s[(t >> 4) * GR_TW2_STRIDE + (t & 15)] = cf{v.x, v.y};
-    }
-    __syncthreads();
-    const cf* tw2 = tw2s + (t & 7) * GR_TW2_STRIDE;
-
-    const float2* spec = a.spec + (size_t)(rec * a.nbins + bin) * a.nnoncoh * GR_N + t;
-    const float sc = (a.mode == GR_ACQ_POW) ? a.scale * a.scale : a.scale;
-
-    for (int g = 0; g < G; ++g) {
-        const int pi = grp * G + g;
-        if (pi >= a.nprn) break;                               // uniform across the CTA
-        const float2* cs = a.tab.conjspec + (size_t)a.prns[pi] * GR_N + t;
-        cf c[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float2 v = __ldg(cs + 128 * j);
-            c[j] = cf{v.x, v.y};
-        }
-        float acc[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-        for (int k = 0; k < a.nnoncoh; ++k) {
-            cf y[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float2 v = __ldg(spec + (size_t)k * GR_N + 128 * j);
-                y[j] = cf{v.x, v.y};
-            }
-            // one prefetch per thread covers the next spectrum: thread t touches its 128-byte line t
-            if (k + 1 < a.nnoncoh)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(spec - t + (size_t)(k + 1) * GR_N + 16 * t));
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                // Y = X * conjC ; operand of the swap-form inverse = (Im Y, Re Y)
-                const cf x = y[j];
-                y[j].x = x.x * c[j].y + x.y * c[j].x;
-                y[j].y = x.x * c[j].x - x.y * c[j].y;
-            }
-            fft2048<true>(y, smem, tw1, tw2, t);
-            if (a.mode == GR_ACQ_POW) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += y[j].x * y[j].x + y[j].y * y[j].y;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += sqrtf(y[j].x * y[j].x + y[j].y * y[j].y);
-            }
-        }
-        // ---- reduce this PRN's 2048 lags to one cell ----
-        float st[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) st[j] = acc[j] * sc;
-        acq_cell_epilogue(st, t, t, a, rec, pi, bin, sh_d, sh_f, sh_i);
-    }
-}
-
-// ---- kernel 2b: the same inverse kernel with per-thread constants parked in tensor memory -------------
-// The FFT butterflies need y[16] + acc[16]; the PRN's conjugate spectrum c[16] and the two twiddle
-// sets are per-thread constants that cost 92 registers and cap the kernel at 3 CTAs / SM.  TMEM (256 KB
-// per SM, otherwise idle here) is lane-private storage with its own datapath: each thread parks its
-// constants in its own TMEM lane (tcgen05.st, shape 32x32b) and streams them back 16 words at a time
-// (tcgen05.ld) right where they are consumed.  TM bit 0: c[], bit 1: stage-2 twiddles, bit 2: stage-1
-// twiddles.  No MMA is issued; TMEM is used purely as a register-file extension.
+// CTA = (recording, Doppler bin, group of G PRNs), PRN groups fastest so that the CTAs sharing a forward
+// spectrum run together and hit it in L2.  The PRN loop and the interval loop are real loops around ONE
+// FFT code path (it stays in the instruction cache).
+//
+// Register file extension in tensor memory: the butterflies need y[16] + acc[16]; the PRN's conjugate
+// spectrum c[16] and the two twiddle sets are per-thread constants that would cost 92 more registers and
+// cap the kernel at 3 CTAs / SM.  TMEM (256 KB per SM, otherwise idle: no MMA is issued here) is
+// lane-private storage with its own datapath (~850 B/clk/SM measured, tools/ubench): each thread parks its
+// constants in its own TMEM lane (tcgen05.st 32x32b) and streams them back 16 words at a time
+// (tcgen05.ld) right where they are consumed.  The same TMEM also carries the FFT's second transpose
+// (gr_fft2048t.cuh).  128 columns per CTA: c | exchange | stage-2 twiddles | stage-1 twiddles => 4 CTAs / SM.
 __device__ __forceinline__ void tm_ld16(uint32_t taddr, float* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
@@ -344,438 +280,11 @@ __device__ __forceinline__ void twiddle8(cf* v, int k0, const cf* tw, uint32_t t
     }
 }
 
-template <int TM>
-__device__ __forceinline__ void fft2048_tm(cf* v, cf* smem, const cf* tw1, const cf* tw2, uint32_t tm_tw1,
-                                           uint32_t tm_tw2, int t) {
-    cf* buf1 = smem;
-    cf* buf2 = smem + GR_B1_ELEMS;
-    dft16(v);
-    twiddle8<(TM & 4) != 0>(v, 0, tw1, tm_tw1);
-    twiddle8<(TM & 4) != 0>(v, 8, tw1, tm_tw1);
-    fft_ex1_write(buf1, t, v);
-    __syncthreads();
-    fft_ex1_read(buf1, t, v);
-    dft16(v);
-    twiddle8<(TM & 2) != 0>(v, 0, tw2, tm_tw2);
-    twiddle8<(TM & 2) != 0>(v, 8, tw2, tm_tw2);
-    fft_ex2_write(buf2, t, v);
-    __syncthreads();
-    fft_ex2_read_stage3(buf2, t, v);
-}
-
-// LD: how the forward spectrum is fetched. 0 = ld.global.nc + prefetch of the next one into L1,
-// 1 = ld.global.nc.L1::no_allocate (no prefetch), 2 = ld.global.cg (L2 only, no prefetch)
-template <int LD>
-__device__ __forceinline__ float2 ld_spec(const float2* p) {
-    float2 v;
-    if (LD == 1) asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    else if (LD == 2) asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    else v = __ldg(p);
-    return v;
-}
-
-template <int G, int TM, int MINB, int LD = 0>
-__global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_tm_kernel(const AcqArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cf* smem = reinterpret_cast<cf*>(smem_raw);
-    cf* tw2s = smem + GR_B1_ELEMS + GR_B2_ELEMS;              // [8][17] (only when tw2 is not in TMEM)
-    __shared__ double sh_d[8];
-    __shared__ float sh_f[4];
-    __shared__ int sh_i[4];
-    __shared__ uint32_t tm_base_sh;
-    constexpr int kCols = ((TM & 1) ? 32 : 0) + ((TM & 2) ? 32 : 0) + ((TM & 4) ? 32 : 0);
-    constexpr int kAlloc = kCols <= 32 ? 32 : (kCols <= 64 ? 64 : 128);
-
-    const int t = threadIdx.x;
-    int id = blockIdx.x;
-    const int grp = id % a.ngroups; id /= a.ngroups;
-    const int bin = id % a.nbins;
-    const int rec = id / a.nbins;
-
-    if (t < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         (uint32_t)__cvta_generic_to_shared(&tm_base_sh)), "r"(kAlloc));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (!(TM & 2)) {
-        const float2 v = a.tab.tw2[t];                         // 8 x 16 entries = 128 threads
-        tw2s[(t >> 4) * GR_TW2_STRIDE + (t & 15)] = cf{v.x, v.y};
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t tm = tm_base_sh + ((uint32_t)(32 * (t >> 5)) << 16);
-    constexpr int kColC = 0, kColTw2 = (TM & 1) ? 32 : 0, kColTw1 = kColTw2 + ((TM & 2) ? 32 : 0);
-
-    cf tw1[(TM & 4) ? 1 : 16];
-    if (TM & 4) {
-        float w[32];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float2 u = a.tab.tw1[t * 16 + i];
-            w[2 * i] = u.x; w[2 * i + 1] = u.y;
-        }
-        tm_st16(tm + kColTw1, w);
-        tm_st16(tm + kColTw1 + 16, w + 16);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float2 u = a.tab.tw1[t * 16 + i];
-            tw1[(TM & 4) ? 0 : i] = cf{u.x, u.y};
-        }
-    }
-    if (TM & 2) {
-        float w[32];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float2 u = a.tab.tw2[(t & 7) * 16 + i];
-            w[2 * i] = u.x; w[2 * i + 1] = u.y;
-        }
-        tm_st16(tm + kColTw2, w);
-        tm_st16(tm + kColTw2 + 16, w + 16);
-    }
-    tm_wait_st();
-    const cf* tw2 = tw2s + (t & 7) * GR_TW2_STRIDE;
-
-    const float2* spec = a.spec + (size_t)(rec * a.nbins + bin) * a.nnoncoh * GR_N + t;
-    const float sc = (a.mode == GR_ACQ_POW) ? a.scale * a.scale : a.scale;
-
-    for (int g = 0; g < G; ++g) {
-        const int pi = grp * G + g;
-        if (pi >= a.nprn) break;                               // uniform across the CTA
-        const float2* cs = a.tab.conjspec + (size_t)a.prns[pi] * GR_N + t;
-        cf c[(TM & 1) ? 1 : 16];
-        if (TM & 1) {
-            float w[32];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float2 v = __ldg(cs + 128 * j);
-                w[2 * j] = v.x; w[2 * j + 1] = v.y;
-            }
-            tm_st16(tm + kColC, w);
-            tm_st16(tm + kColC + 16, w + 16);
-            tm_wait_st();
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float2 v = __ldg(cs + 128 * j);
-                c[(TM & 1) ? 0 : j] = cf{v.x, v.y};
-            }
-        }
-        float acc[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-        for (int k = 0; k < a.nnoncoh; ++k) {
-            cf y[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float2 v = ld_spec<LD>(spec + (size_t)k * GR_N + 128 * j);
-                y[j] = cf{v.x, v.y};
-            }
-            if (LD == 0 && k + 1 < a.nnoncoh)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(spec - t + (size_t)(k + 1) * GR_N + 16 * t));
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float w[16];
-                if (TM & 1) tm_ld16(tm + kColC + 16 * h, w);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const cf cc = (TM & 1) ? cf{w[2 * j], w[2 * j + 1]} : c[(TM & 1) ? 0 : 8 * h + j];
-                    const cf x = y[8 * h + j];
-                    y[8 * h + j].x = x.x * cc.y + x.y * cc.x;
-                    y[8 * h + j].y = x.x * cc.x - x.y * cc.y;
-                }
-            }
-            fft2048_tm<TM>(y, smem, tw1, tw2, tm + kColTw1, tm + kColTw2, t);
-            if (a.mode == GR_ACQ_POW) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += y[j].x * y[j].x + y[j].y * y[j].y;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += sqrtf(y[j].x * y[j].x + y[j].y * y[j].y);
-            }
-        }
-        float st[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) st[j] = acc[j] * sc;
-        acq_cell_epilogue(st, t, t, a, rec, pi, bin, sh_d, sh_f, sh_i);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    if (t < 32)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base_sh), "r"(kAlloc));
-}
-
-// ---- kernel 2c: inverse kernel, generation 3 ---------------------------------------------------------
-// gr_fft2048w.cuh transposes (128-bit stores, warp-local second exchange, ONE block barrier per FFT on a
-// double-buffered exchange-1 buffer), forward spectra fetched as 8 x 128-bit from the paired layout,
-// c[] and the stage-2 twiddles (TM bit 1) / stage-1 twiddles (TM bit 2) in TMEM.
-template <int G, int TM, int MINB>
-__global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv3_kernel(const AcqArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* buf1 = reinterpret_cast<float4*>(smem_raw);                         // 2 x 16 KiB
-    __shared__ double sh_d[8];
-    __shared__ float sh_f[4];
-    __shared__ int sh_i[4];
-    __shared__ uint32_t tm_base_sh;
-    constexpr int kCols = 32 + ((TM & 2) ? 32 : 0) + ((TM & 4) ? 32 : 0);
-    constexpr int kAlloc = kCols <= 32 ? 32 : (kCols <= 64 ? 64 : 128);
-    constexpr int kColC = 0, kColTw2 = 32, kColTw1 = kColTw2 + ((TM & 2) ? 32 : 0);
-
-    const int t = threadIdx.x, l = t & 31;
-    cf* buf2w = reinterpret_cast<cf*>(smem_raw + 2 * GR_W_BUF1_BYTES) + (t >> 5) * GR_W_WARP_UNITS;
-    int id = blockIdx.x;
-    const int grp = id % a.ngroups; id /= a.ngroups;
-    const int bin = id % a.nbins;
-    const int rec = id / a.nbins;
-
-    if (t < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         (uint32_t)__cvta_generic_to_shared(&tm_base_sh)), "r"(kAlloc));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t tm = tm_base_sh + ((uint32_t)(32 * (t >> 5)) << 16);
-
-    cf tw1[(TM & 4) ? 1 : 16], tw2[(TM & 2) ? 1 : 16];
-    {
-        float w[32];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float2 u = a.tab.tw1[t * 16 + i];
-            w[2 * i] = u.x; w[2 * i + 1] = u.y;
-            if (!(TM & 4)) tw1[(TM & 4) ? 0 : i] = cf{u.x, u.y};
-        }
-        if (TM & 4) { tm_st16(tm + kColTw1, w); tm_st16(tm + kColTw1 + 16, w + 16); }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float2 u = a.tab.tw2[(t & 7) * 16 + i];
-            w[2 * i] = u.x; w[2 * i + 1] = u.y;
-            if (!(TM & 2)) tw2[(TM & 2) ? 0 : i] = cf{u.x, u.y};
-        }
-        if (TM & 2) { tm_st16(tm + kColTw2, w); tm_st16(tm + kColTw2 + 16, w + 16); }
-    }
-
-    const float4* spec = reinterpret_cast<const float4*>(a.spec + (size_t)(rec * a.nbins + bin) * a.nnoncoh * GR_N) + t;
-    const float sc = (a.mode == GR_ACQ_POW) ? a.scale * a.scale : a.scale;
-    const int obase = fftw_out_base(t);
-    int par = 0;                                               // exchange-1 buffer of the next transform
-
-    for (int g = 0; g < G; ++g) {
-        const int pi = grp * G + g;
-        if (pi >= a.nprn) break;                               // uniform across the CTA
-        {
-            const float2* cs = a.tab.conjspec + (size_t)a.prns[pi] * GR_N + t;
-            float w[32];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float2 v = __ldg(cs + 128 * j);
-                w[2 * j] = v.x; w[2 * j + 1] = v.y;
-            }
-            tm_st16(tm + kColC, w);
-            tm_st16(tm + kColC + 16, w + 16);
-            tm_wait_st();
-        }
-        float acc[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-        for (int k = 0; k < a.nnoncoh; ++k) {
-            cf y[16];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const float4 v = __ldg(spec + (size_t)k * (GR_N / 2) + 128 * m);
-                y[2 * m] = cf{v.x, v.y};
-                y[2 * m + 1] = cf{v.z, v.w};
-            }
-            if (k + 1 < a.nnoncoh)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(spec - t) +
-                                                                 (size_t)(k + 1) * GR_N * 8 + 128 * t));
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float w[16];
-                tm_ld16(tm + kColC + 16 * h, w);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    // Y = X * conjC ; operand of the swap-form inverse = (Im Y, Re Y)
-                    const cf cc = cf{w[2 * j], w[2 * j + 1]};
-                    const cf x = y[8 * h + j];
-                    y[8 * h + j].x = x.x * cc.y + x.y * cc.x;
-                    y[8 * h + j].y = x.x * cc.x - x.y * cc.y;
-                }
-            }
-            // ---- FFT-2048 (gr_fft2048w.cuh) ----
-            dft16(y);
-            twiddle8<(TM & 4) != 0>(y, 0, tw1, tm + kColTw1);
-            twiddle8<(TM & 4) != 0>(y, 8, tw1, tm + kColTw1);
-            float4* b1 = buf1 + par * (GR_W_BUF1_BYTES / 16);
-            par ^= 1;
-            fftw_ex1_write(b1, t, y);
-            __syncthreads();
-            fftw_ex1_read(b1, t, y);
-            dft16(y);
-            twiddle8<(TM & 2) != 0>(y, 0, tw2, tm + kColTw2);
-            twiddle8<(TM & 2) != 0>(y, 8, tw2, tm + kColTw2);
-            fftw_ex2_write(buf2w, l, y);
-            __syncwarp();
-            fftw_ex2_read_stage3(buf2w, l, y);
-            __syncwarp();
-            if (a.mode == GR_ACQ_POW) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += y[j].x * y[j].x + y[j].y * y[j].y;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += sqrtf(y[j].x * y[j].x + y[j].y * y[j].y);
-            }
-        }
-        float st[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) st[j] = acc[j] * sc;
-        acq_cell_epilogue(st, obase, t, a, rec, pi, bin, sh_d, sh_f, sh_i);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    if (t < 32)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base_sh), "r"(kAlloc));
-}
-
-// ---- kernel 2d: inverse kernel, generation 4: second exchange through TMEM (gr_fft2048t.cuh) ------------
-// gr_fft2048w.cuh transposes (128-bit stores, warp-local second exchange, ONE block barrier per FFT on a
-// double-buffered exchange-1 buffer), forward spectra fetched as 8 x 128-bit from the paired layout,
-// c[] and the stage-2 twiddles (TM bit 1) / stage-1 twiddles (TM bit 2) in TMEM.
-template <int G, int TM, int MINB>
-__global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv4_kernel(const AcqArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* buf1 = reinterpret_cast<float4*>(smem_raw);                         // 2 x 16 KiB
-    __shared__ double sh_d[8];
-    __shared__ float sh_f[4];
-    __shared__ int sh_i[4];
-    __shared__ uint32_t tm_base_sh;
-    constexpr int kCols = 64 + ((TM & 2) ? 32 : 0) + ((TM & 4) ? 32 : 0);
-    constexpr int kAlloc = kCols <= 32 ? 32 : (kCols <= 64 ? 64 : 128);
-    constexpr int kColC = 0, kColX = 32, kColTw2 = 64, kColTw1 = kColTw2 + ((TM & 2) ? 32 : 0);
-
-    const int t = threadIdx.x;
-    int id = blockIdx.x;
-    const int grp = id % a.ngroups; id /= a.ngroups;
-    const int bin = id % a.nbins;
-    const int rec = id / a.nbins;
-
-    if (t < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         (uint32_t)__cvta_generic_to_shared(&tm_base_sh)), "r"(kAlloc));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t tm = tm_base_sh + ((uint32_t)(32 * (t >> 5)) << 16);
-
-    cf tw1[(TM & 4) ? 1 : 16], tw2[(TM & 2) ? 1 : 16];
-    {
-        float w[32];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float2 u = a.tab.tw1[t * 16 + i];
-            w[2 * i] = u.x; w[2 * i + 1] = u.y;
-            if (!(TM & 4)) tw1[(TM & 4) ? 0 : i] = cf{u.x, u.y};
-        }
-        if (TM & 4) { tm_st16(tm + kColTw1, w); tm_st16(tm + kColTw1 + 16, w + 16); }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float2 u = a.tab.tw2[fftt_n3(t) * 16 + i];
-            w[2 * i] = u.x; w[2 * i + 1] = u.y;
-            if (!(TM & 2)) tw2[(TM & 2) ? 0 : i] = cf{u.x, u.y};
-        }
-        if (TM & 2) { tm_st16(tm + kColTw2, w); tm_st16(tm + kColTw2 + 16, w + 16); }
-    }
-
-    const float4* spec = reinterpret_cast<const float4*>(a.spec + (size_t)(rec * a.nbins + bin) * a.nnoncoh * GR_N) + t;
-    const float sc = (a.mode == GR_ACQ_POW) ? a.scale * a.scale : a.scale;
-    const int obase = fftt_out_base(t);
-    int par = 0;                                               // exchange-1 buffer of the next transform
-
-    for (int g = 0; g < G; ++g) {
-        const int pi = grp * G + g;
-        if (pi >= a.nprn) break;                               // uniform across the CTA
-        {
-            const float2* cs = a.tab.conjspec + (size_t)a.prns[pi] * GR_N + t;
-            float w[32];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float2 v = __ldg(cs + 128 * j);
-                w[2 * j] = v.x; w[2 * j + 1] = v.y;
-            }
-            tm_st16(tm + kColC, w);
-            tm_st16(tm + kColC + 16, w + 16);
-            tm_wait_st();
-        }
-        float acc[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-        for (int k = 0; k < a.nnoncoh; ++k) {
-            cf y[16];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const float4 v = __ldg(spec + (size_t)k * (GR_N / 2) + 128 * m);
-                y[2 * m] = cf{v.x, v.y};
-                y[2 * m + 1] = cf{v.z, v.w};
-            }
-            if (k + 1 < a.nnoncoh)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(spec - t) +
-                                                                 (size_t)(k + 1) * GR_N * 8 + 128 * t));
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float w[16];
-                tm_ld16(tm + kColC + 16 * h, w);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    // Y = X * conjC ; operand of the swap-form inverse = (Im Y, Re Y)
-                    const cf cc = cf{w[2 * j], w[2 * j + 1]};
-                    const cf x = y[8 * h + j];
-                    y[8 * h + j].x = x.x * cc.y + x.y * cc.x;
-                    y[8 * h + j].y = x.x * cc.x - x.y * cc.y;
-                }
-            }
-            // ---- FFT-2048 (gr_fft2048w.cuh) ----
-            dft16(y);
-            twiddle8<(TM & 4) != 0>(y, 0, tw1, tm + kColTw1);
-            twiddle8<(TM & 4) != 0>(y, 8, tw1, tm + kColTw1);
-            float4* b1 = buf1 + par * (GR_W_BUF1_BYTES / 16);
-            par ^= 1;
-            fftw_ex1_write(b1, t, y);
-            __syncthreads();
-            fftt_ex1_read(b1, t, y);
-            dft16(y);
-            twiddle8<(TM & 2) != 0>(y, 0, tw2, tm + kColTw2);
-            twiddle8<(TM & 2) != 0>(y, 8, tw2, tm + kColTw2);
-            fftt_ex2_stage3(tm + kColX, y);
-            if (a.mode == GR_ACQ_POW) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += y[j].x * y[j].x + y[j].y * y[j].y;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += sqrtf(y[j].x * y[j].x + y[j].y * y[j].y);
-            }
-        }
-        float st[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) st[j] = acc[j] * sc;
-        acq_cell_epilogue(st, obase, t, a, rec, pi, bin, sh_d, sh_f, sh_i);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    if (t < 32)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base_sh), "r"(kAlloc));
-}
-
-// ---- kernel 2e: generation 5 = generation 4 + forward spectra staged by TMA ---------------------------------
-// ncu (profiles/): the largest stall of generation 4 is the wait for the forward spectrum X_k (global ->
-// registers at the top of every transform).  Here one thread issues a 16 KiB cp.async.bulk (TMA) for X_{k+1}
-// into a shared-memory stage right after the exchange-1 barrier of transform k (every thread has consumed X_k
-// by then), completion is tracked by an mbarrier, and the conjugate code spectrum is fetched from TMEM before
-// the wait.  No registers are held across the transform for the prefetch.
+// Forward spectra staged by TMA: one thread issues a 16 KiB cp.async.bulk for X_{k+1} into a shared-memory
+// stage right after the exchange-1 barrier of transform k (every thread has consumed X_k by then); completion
+// is tracked by an mbarrier, and the conjugate code spectrum is fetched from TMEM before the wait.  No
+// registers are held across the transform for the prefetch (ncu: the wait for X_k was the largest stall of
+// the register-fed version).
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -807,11 +316,12 @@ __device__ __forceinline__ void tm_ld_wait16(float* r) {      // the registers b
                    "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]));
 }
 
-// gr_fft2048w.cuh transposes (128-bit stores, warp-local second exchange, ONE block barrier per FFT on a
-// double-buffered exchange-1 buffer), forward spectra fetched as 8 x 128-bit from the paired layout,
-// c[] and the stage-2 twiddles (TM bit 1) / stage-1 twiddles (TM bit 2) in TMEM.
+// FFT: gr_fft2048t.cuh (exchange 1 in shared memory with 128-bit stores on a double-buffered 16 KiB buffer and
+// ONE block barrier per transform; exchange 2 + radix-8 through TMEM).  TM bit 1 / bit 2: stage-2 / stage-1
+// twiddles in TMEM (else registers).
+#define GR_ACQ_INV_SMEM (3 * GR_W_BUF1_BYTES)      // 2 x exchange-1 buffer + forward-spectrum stage = 48 KiB
 template <int G, int TM, int MINB>
-__global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv5_kernel(const AcqArgs a) {
+__global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const AcqArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* buf1 = reinterpret_cast<float4*>(smem_raw);                         // 2 x 16 KiB
     float4* xs = reinterpret_cast<float4*>(smem_raw + 2 * GR_W_BUF1_BYTES);      // forward-spectrum stage, 16 KiB
@@ -911,7 +421,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv5_kernel(const Ac
                 y[8 + j].x = x1.x * c1.y + x1.y * c1.x;
                 y[8 + j].y = x1.x * c1.x - x1.y * c1.y;
             }
-            // ---- FFT-2048 (gr_fft2048w.cuh) ----
+            // ---- FFT-2048 (gr_fft2048t.cuh) ----
             dft16(y);
             twiddle8<(TM & 4) != 0>(y, 0, tw1, tm + kColTw1);
             twiddle8<(TM & 4) != 0>(y, 8, tw1, tm + kColTw1);
@@ -1002,7 +512,6 @@ static int grow(void** ptr, size_t* have, size_t need) {
 }
 
 #define GR_ACQ_SPEC_CAP (8ull << 30)     // scratch for forward spectra: at most 8 GiB per sub-batch
-#define GR_ACQ_INV_SMEM (GR_FFT_SMEM_BYTES + 8 * GR_TW2_STRIDE * 8)
 
 extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, int64_t rec_stride,
                               gr_acq_cell* d_out, void* stream) {
@@ -1019,48 +528,12 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
     int rc = grow((void**)&p->d_spec, &p->spec_bytes, (size_t)sub * spec_per_rec);
     if (rc != GR_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    void (*fwd)(const AcqArgs) = p->in_format == GR_IN_U8IQ ? acq_fwd_kernel<GR_IN_U8IQ> : acq_fwd_kernel<GR_IN_CF32>;
-    // GPSB200_ACQ_VARIANT (development switch): 0 = registers only, else TM bitmask | MINB << 4
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("GPSB200_ACQ_VARIANT"); variant = e ? atoi(e) : 0; }
-    void (*inv)(const AcqArgs) = acq_inv_kernel<GR_ACQ_G>;
-    bool gen3 = false;
-    size_t inv_smem = GR_ACQ_INV_SMEM;
-    switch (variant) {
-        case 0x41: inv = acq_inv_tm_kernel<GR_ACQ_G, 1, 4>; break;
-        case 0x43: inv = acq_inv_tm_kernel<GR_ACQ_G, 3, 4>; break;
-        case 0x45: inv = acq_inv_tm_kernel<GR_ACQ_G, 5, 4>; break;
-        case 0x55: inv = acq_inv_tm_kernel<GR_ACQ_G, 5, 5>; break;
-        case 0x47: inv = acq_inv_tm_kernel<GR_ACQ_G, 7, 4>; break;
-        case 0x53: inv = acq_inv_tm_kernel<GR_ACQ_G, 3, 5>; break;
-        case 0x143: inv = acq_inv_tm_kernel<GR_ACQ_G, 3, 4, 1>; break;
-        case 0x243: inv = acq_inv_tm_kernel<GR_ACQ_G, 3, 4, 2>; break;
-        case 0x155: inv = acq_inv_tm_kernel<GR_ACQ_G, 5, 5, 1>; break;
-        case 0x255: inv = acq_inv_tm_kernel<GR_ACQ_G, 5, 5, 2>; break;
-        case 0x65: inv = acq_inv_tm_kernel<GR_ACQ_G, 5, 6>; break;
-        case 0x67: inv = acq_inv_tm_kernel<GR_ACQ_G, 7, 6>; break;
-        case 0x33: inv = acq_inv_tm_kernel<GR_ACQ_G, 3, 3>; break;
-        case 0x1041: inv = acq_inv3_kernel<GR_ACQ_G, 0, 4>; gen3 = true; break;
-        case 0x1043: inv = acq_inv3_kernel<GR_ACQ_G, 2, 4>; gen3 = true; break;
-        case 0x1045: inv = acq_inv3_kernel<GR_ACQ_G, 4, 4>; gen3 = true; break;
-        case 0x1047: inv = acq_inv3_kernel<GR_ACQ_G, 6, 4>; gen3 = true; break;
-        case 0x1033: inv = acq_inv3_kernel<GR_ACQ_G, 2, 3>; gen3 = true; break;
-        case 0x2041: inv = acq_inv4_kernel<GR_ACQ_G, 0, 4>; gen3 = true; inv_smem = 2 * GR_W_BUF1_BYTES; break;
-        case 0x2043: inv = acq_inv4_kernel<GR_ACQ_G, 2, 4>; gen3 = true; inv_smem = 2 * GR_W_BUF1_BYTES; break;
-        case 0x2045: inv = acq_inv4_kernel<GR_ACQ_G, 4, 4>; gen3 = true; inv_smem = 2 * GR_W_BUF1_BYTES; break;
-        case 0x2047: inv = acq_inv4_kernel<GR_ACQ_G, 6, 4>; gen3 = true; inv_smem = 2 * GR_W_BUF1_BYTES; break;
-        case 0x2033: inv = acq_inv4_kernel<GR_ACQ_G, 2, 3>; gen3 = true; inv_smem = 2 * GR_W_BUF1_BYTES; break;
-        case 0x3047: inv = acq_inv5_kernel<GR_ACQ_G, 6, 4>; gen3 = true; inv_smem = 3 * GR_W_BUF1_BYTES; break;
-        case 0x3045: inv = acq_inv5_kernel<GR_ACQ_G, 4, 4>; gen3 = true; inv_smem = 3 * GR_W_BUF1_BYTES; break;
-        case 0x3043: inv = acq_inv5_kernel<GR_ACQ_G, 2, 4>; gen3 = true; inv_smem = 3 * GR_W_BUF1_BYTES; break;
-        default: break;
-    }
-    if (gen3) {
-        fwd = p->in_format == GR_IN_U8IQ ? acq_fwd_kernel<GR_IN_U8IQ, true> : acq_fwd_kernel<GR_IN_CF32, true>;
-        if (variant < 0x2000) inv_smem = GR_W_SMEM_BYTES;
-    }
+    const bool one = p->tcoh == 1;
+    void (*fwd)(const AcqArgs) = p->in_format == GR_IN_U8IQ ? (one ? acq_fwd_kernel<GR_IN_U8IQ, true> : acq_fwd_kernel<GR_IN_U8IQ, false>)
+                                                            : (one ? acq_fwd_kernel<GR_IN_CF32, true> : acq_fwd_kernel<GR_IN_CF32, false>);
+    void (*inv)(const AcqArgs) = acq_inv_kernel<GR_ACQ_G, 6, 4>;
     GR_CUDA(cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_FFT_SMEM_BYTES));
-    GR_CUDA(cudaFuncSetAttribute(inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
+    GR_CUDA(cudaFuncSetAttribute(inv, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_ACQ_INV_SMEM));
     const size_t bps = p->in_format == GR_IN_U8IQ ? 2 : 8;
     p->last_launches = 0;
     for (int r0 = 0; r0 < nrec; r0 += sub) {
@@ -1080,11 +553,18 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         a.out = d_out + (size_t)r0 * p->nprn * p->nbins;
         a.spec = p->d_spec;
         a.tab = gr_lib()->tab;
-        const long long nfwd = (long long)nr * p->nbins * p->nnoncoh;
+        // forward grid: enough CTAs to fill the GPU a few times over, as many bins per CTA as that allows
+        const long long units = (long long)nr * p->nnoncoh;
+        long long nchunks = (4LL * gr_lib()->num_sms * 4 + units - 1) / units;
+        if (nchunks > p->nbins) nchunks = p->nbins;
+        if (nchunks < 1) nchunks = 1;
+        a.bins_per_chunk = (int)((p->nbins + nchunks - 1) / nchunks);
+        a.nchunks = (p->nbins + a.bins_per_chunk - 1) / a.bins_per_chunk;
+        const long long nfwd = units * a.nchunks;
         const long long ninv = (long long)nr * p->nbins * a.ngroups;
         if (nfwd > 0x7fffffffLL || ninv > 0x7fffffffLL) { gr_set_error("gr_acq_run_dev: grid too large"); return GR_ERR_ARG; }
         fwd<<<(unsigned)nfwd, GR_FFT_THREADS, GR_FFT_SMEM_BYTES, s>>>(a);
-        inv<<<(unsigned)ninv, GR_FFT_THREADS, inv_smem, s>>>(a);
+        inv<<<(unsigned)ninv, GR_FFT_THREADS, GR_ACQ_INV_SMEM, s>>>(a);
         GR_CUDA(cudaGetLastError());
         p->last_launches += 2;
     }
