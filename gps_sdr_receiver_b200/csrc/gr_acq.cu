@@ -42,7 +42,7 @@ struct AcqArgs {
     long long rec_stride;      // samples
     const int32_t* prns;
     const float* w32;
-    int nprn, nbins, ngroups, tcoh, nnoncoh, mode;
+    int nrec, nprn, nbins, ngroups, tcoh, nnoncoh, mode;
     int nchunks, bins_per_chunk;   // forward kernel: Doppler bins per CTA
     float scale;               // 1 / (tcoh * 2048)
     gr_acq_cell* out;
@@ -81,7 +81,9 @@ struct BlockStat {
     int idx;
 };
 
-// all 128 threads get the CTA-wide result
+// CTA-wide statistics of 2048 values held 16 per thread (value j of this thread = lag nb + 128 j).
+// One barrier; every thread gets the result.  sh_* are 4-entry scratch arrays that the caller must not
+// reuse before its next block barrier.
 __device__ __forceinline__ BlockStat block_stats(const float* st, int nb, int t, double* sh_d, float* sh_f, int* sh_i) {
     float s = 0.f, s2 = 0.f, mx = -1.f;
     int idx = 0;
@@ -113,17 +115,6 @@ __device__ __forceinline__ BlockStat block_stats(const float* st, int nb, int t,
         const int oi = sh_i[k];
         if (om > r.mx || (om == r.mx && oi < r.idx)) { r.mx = om; r.idx = oi; }
     }
-    __syncthreads();
-    return r;
-}
-
-__device__ __forceinline__ float block_max(float v, int t, float* sh_f) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if ((t & 31) == 0) sh_f[t >> 5] = v;
-    __syncthreads();
-    const float r = fmaxf(fmaxf(sh_f[0], sh_f[1]), fmaxf(sh_f[2], sh_f[3]));
-    __syncthreads();
     return r;
 }
 
@@ -198,12 +189,18 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
     }
 }
 
-// reduce one PRN's 2048 scaled lags (st[j] = lag t + 128 j) to its gr_acq_cell
-// (st[j] = lag nb + 128 j; nb = t for the gr_fft2048.cuh layout, fftw_out_base(t) for gr_fft2048w.cuh)
-__device__ __forceinline__ void acq_cell_epilogue(const float* st, int nb, int t, const AcqArgs& a, int rec, int pi, int bin,
-                                                  double* sh_d, float* sh_f, int* sh_i) {
-    const BlockStat bs = block_stats(st, nb, t, sh_d, sh_f, sh_i);
+// reduce one PRN's 2048 scaled lags (st[j] = lag nb + 128 j; nb = fftt_out_base(t)) to its gr_acq_cell.
+// Two block barriers; the scratch arrays are free again after the caller's next block barrier.
+struct AcqScratch {
+    double d[8];
+    float f[4];
+    int i[4];
+    float sec[4];
+};
+__device__ __forceinline__ void acq_cell_epilogue(const float* st, int nb, int t, gr_acq_cell* cell, AcqScratch* S) {
+    const BlockStat bs = block_stats(st, nb, t, S->d, S->f, S->i);
     const int mx = bs.idx;
+    const int lo = (mx + GR_N - 1) & (GR_N - 1), hi = (mx + 1) & (GR_N - 1);
     float sec = -1.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -212,16 +209,13 @@ __device__ __forceinline__ void acq_cell_epilogue(const float* st, int nb, int t
         d = d < 0 ? -d : d;
         d = d > GR_N / 2 ? GR_N - d : d;
         if (d > GR_SECOND_PEAK_GUARD) sec = fmaxf(sec, st[j]);
-    }
-    sec = block_max(sec, t, sh_f);
-    gr_acq_cell* cell = a.out + ((size_t)rec * a.nprn + pi) * a.nbins + bin;
-    const int lo = (mx + GR_N - 1) & (GR_N - 1), hi = (mx + 1) & (GR_N - 1);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int n = nb + 128 * j;
         if (n == lo) cell->em1 = st[j];
         if (n == hi) cell->ep1 = st[j];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sec = fmaxf(sec, __shfl_xor_sync(0xffffffffu, sec, o));
+    if ((t & 31) == 0) S->sec[t >> 5] = sec;
+    __syncthreads();
     if (t == 0) {
         const double mean = bs.sum / GR_N;
         double var = bs.sum2 / GR_N - mean * mean;
@@ -232,7 +226,7 @@ __device__ __forceinline__ void acq_cell_epilogue(const float* st, int nb, int t
         cell->mean = (float)mean;
         cell->std = (float)sd;
         cell->z = (float)(((double)bs.mx - mean) / sd);
-        cell->second = sec;
+        cell->second = fmaxf(fmaxf(S->sec[0], S->sec[1]), fmaxf(S->sec[2], S->sec[3]));
     }
 }
 
@@ -319,26 +313,30 @@ __device__ __forceinline__ void tm_ld_wait16(float* r) {      // the registers b
 // FFT: gr_fft2048t.cuh (exchange 1 in shared memory with 128-bit stores on a double-buffered 16 KiB buffer and
 // ONE block barrier per transform; exchange 2 + radix-8 through TMEM).  TM bit 1 / bit 2: stage-2 / stage-1
 // twiddles in TMEM (else registers).
-#define GR_ACQ_INV_SMEM (3 * GR_W_BUF1_BYTES)      // 2 x exchange-1 buffer + forward-spectrum stage = 48 KiB
+#define GR_ACQ_INV_SMEM (3 * GR_W_BUF1_BYTES + GR_N * 2)   // 2 x exchange-1 buffer + forward-spectrum stage + 8 of 16 accumulators = 52 KiB
+// Persistent: the grid is 4 CTAs per SM; a CTA walks over work items (recording, Doppler bin, PRN group) with a
+// grid stride, keeping its TMEM allocation and twiddles.  One "job" = one PRN of a work item = nnoncoh
+// transforms.  The next job's conjugate spectrum is loaded from L2 while the current job's cell statistics
+// are being reduced, and the next job's first forward spectrum is already in flight (TMA) by then.
 template <int G, int TM, int MINB>
 __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const AcqArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* buf1 = reinterpret_cast<float4*>(smem_raw);                         // 2 x 16 KiB
     float4* xs = reinterpret_cast<float4*>(smem_raw + 2 * GR_W_BUF1_BYTES);      // forward-spectrum stage, 16 KiB
+    // non-coherent accumulators: 8 of the 16 per thread live in shared memory ([2][128] float4, thread-private
+    // slots) -- at the 128-register cap of 4 CTAs / SM ptxas was spilling accumulators to local memory, and
+    // all 16 in shared memory would not leave room for 4 CTAs (4 x 57 KiB > 228 KiB)
+    float4* accs = reinterpret_cast<float4*>(smem_raw + 3 * GR_W_BUF1_BYTES) + threadIdx.x;
     __shared__ __align__(8) uint64_t xbar;
-    __shared__ double sh_d[8];
-    __shared__ float sh_f[4];
-    __shared__ int sh_i[4];
+    __shared__ AcqScratch scratch;
     __shared__ uint32_t tm_base_sh;
     constexpr int kCols = 64 + ((TM & 2) ? 32 : 0) + ((TM & 4) ? 32 : 0);
-    constexpr int kAlloc = kCols <= 32 ? 32 : (kCols <= 64 ? 64 : 128);
+    constexpr int kAlloc = kCols <= 64 ? 64 : 128;
     constexpr int kColC = 0, kColX = 32, kColTw2 = 64, kColTw1 = kColTw2 + ((TM & 2) ? 32 : 0);
 
     const int t = threadIdx.x;
-    int id = blockIdx.x;
-    const int grp = id % a.ngroups; id /= a.ngroups;
-    const int bin = id % a.nbins;
-    const int rec = id / a.nbins;
+    const int nwork = a.nrec * a.nbins * a.ngroups;
+    int work = blockIdx.x;                                     // host guarantees gridDim.x <= nwork
 
     if (t == 0) mbar_init(&xbar, 1);
     if (t < 32) {
@@ -350,6 +348,12 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tm = tm_base_sh + ((uint32_t)(32 * (t >> 5)) << 16);
+
+    // work item -> (recording, bin, group); PRN groups fastest
+    int grp = work % a.ngroups, bin = (work / a.ngroups) % a.nbins, rec = work / (a.ngroups * a.nbins);
+    const size_t spec_stride = (size_t)a.nnoncoh * GR_N * 8;                     // bytes per (recording, bin)
+    const char* spec = reinterpret_cast<const char*>(a.spec) + (size_t)(work / a.ngroups) * spec_stride;
+    if (t == 0) tma_load_1d(xs, spec, GR_N * 8, &xbar);
 
     cf tw1[(TM & 4) ? 1 : 16], tw2[(TM & 2) ? 1 : 16];
     {
@@ -368,41 +372,33 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             if (!(TM & 2)) tw2[(TM & 2) ? 0 : i] = cf{u.x, u.y};
         }
         if (TM & 2) { tm_st16(tm + kColTw2, w); tm_st16(tm + kColTw2 + 16, w + 16); }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {                          // first job's conjugate code spectrum
+            const float2 v = __ldg(a.tab.conjspec + (size_t)a.prns[grp * G] * GR_N + t + 128 * j);
+            w[2 * j] = v.x; w[2 * j + 1] = v.y;
+        }
+        tm_st16(tm + kColC, w);
+        tm_st16(tm + kColC + 16, w + 16);
+        tm_wait_st();
     }
 
-    const char* spec = reinterpret_cast<const char*>(a.spec + (size_t)(rec * a.nbins + bin) * a.nnoncoh * GR_N);
-    const int ng = (a.nprn - grp * G) < G ? (a.nprn - grp * G) : G;            // PRNs of this CTA
-    const int n_it = ng * a.nnoncoh;
-    int it = 0;                                                                // flattened (PRN, interval) counter
-    if (t == 0 && n_it > 0) tma_load_1d(xs, spec, GR_N * 8, &xbar);
     const float sc = (a.mode == GR_ACQ_POW) ? a.scale * a.scale : a.scale;
     const int obase = fftt_out_base(t);
-    int par = 0;                                               // exchange-1 buffer of the next transform
+    int par = 0;                       // parity of the transforms done so far: exchange-1 buffer AND mbarrier phase
+    int g = 0;
 
-    for (int g = 0; g < G; ++g) {
-        const int pi = grp * G + g;
-        if (pi >= a.nprn) break;                               // uniform across the CTA
-        {
-            const float2* cs = a.tab.conjspec + (size_t)a.prns[pi] * GR_N + t;
-            float w[32];
+    while (true) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float2 v = __ldg(cs + 128 * j);
-                w[2 * j] = v.x; w[2 * j + 1] = v.y;
-            }
-            tm_st16(tm + kColC, w);
-            tm_st16(tm + kColC + 16, w + 16);
-            tm_wait_st();
-        }
-        float acc[16];
+        for (int q = 0; q < 2; ++q) accs[128 * q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float accr[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        for (int j = 0; j < 8; ++j) accr[j] = 0.f;
         for (int k = 0; k < a.nnoncoh; ++k) {
             cf y[16];
             float w0[16], w1[16];
             tm_ld16_issue(tm + kColC, w0);
             tm_ld16_issue(tm + kColC + 16, w1);
-            mbar_wait(&xbar, it & 1);
+            mbar_wait(&xbar, par);
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 const float4 v = xs[128 * m + t];
@@ -429,26 +425,70 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             par ^= 1;
             fftw_ex1_write(b1, t, y);
             __syncthreads();
-            ++it;
-            if (t == 0 && it < n_it)                             // every thread has consumed X_k: refill the stage
-                tma_load_1d(xs, spec + (size_t)(it % a.nnoncoh) * (GR_N * 8), GR_N * 8, &xbar);
+            if (t == 0) {                                        // every thread has consumed X_k: refill the stage
+                if (k + 1 < a.nnoncoh) {
+                    tma_load_1d(xs, spec + (size_t)(k + 1) * (GR_N * 8), GR_N * 8, &xbar);
+                } else {                                         // first spectrum of the next job (same bin or next work item)
+                    int nw = work;
+                    if (g + 1 >= G || grp * G + g + 1 >= a.nprn) nw += gridDim.x;
+                    if (nw < nwork) tma_load_1d(xs, reinterpret_cast<const char*>(a.spec) + (size_t)(nw / a.ngroups) * spec_stride,
+                                                GR_N * 8, &xbar);
+                }
+            }
             fftt_ex1_read(b1, t, y);
             dft16(y);
             twiddle8<(TM & 2) != 0>(y, 0, tw2, tm + kColTw2);
             twiddle8<(TM & 2) != 0>(y, 8, tw2, tm + kColTw2);
             fftt_ex2_stage3(tm + kColX, y);
+            float p[16];
             if (a.mode == GR_ACQ_POW) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += y[j].x * y[j].x + y[j].y * y[j].y;
+                for (int j = 0; j < 16; ++j) p[j] = y[j].x * y[j].x + y[j].y * y[j].y;
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += sqrtf(y[j].x * y[j].x + y[j].y * y[j].y);
+                for (int j = 0; j < 16; ++j) p[j] = sqrtf(y[j].x * y[j].x + y[j].y * y[j].y);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float4 v = accs[128 * q];
+                v.x += p[4 * q]; v.y += p[4 * q + 1]; v.z += p[4 * q + 2]; v.w += p[4 * q + 3];
+                accs[128 * q] = v;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) accr[j] += p[8 + j];
+        }
+        // the job after this one; its conjugate spectrum is loaded now: L2 latency hidden behind the cell reduction
+        int n_work = work, n_g = g + 1;
+        if (n_g >= G || grp * G + n_g >= a.nprn) { n_g = 0; n_work = work + gridDim.x; }
+        const bool has_next = n_work < nwork;
+        const int n_grp = n_work % a.ngroups;
+        float w[32];
+        if (has_next) {
+            const float2* cs = a.tab.conjspec + (size_t)a.prns[n_grp * G + n_g] * GR_N + t;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float2 v = __ldg(cs + 128 * j);
+                w[2 * j] = v.x; w[2 * j + 1] = v.y;
             }
         }
-        float st[16];
+        float acc[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) st[j] = acc[j] * sc;
-        acq_cell_epilogue(st, obase, t, a, rec, pi, bin, sh_d, sh_f, sh_i);
+        for (int q = 0; q < 2; ++q) {
+            const float4 v = accs[128 * q];
+            acc[4 * q] = v.x * sc; acc[4 * q + 1] = v.y * sc; acc[4 * q + 2] = v.z * sc; acc[4 * q + 3] = v.w * sc;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[8 + j] = accr[j] * sc;
+        acq_cell_epilogue(acc, obase, t, a.out + ((size_t)rec * a.nprn + grp * G + g) * a.nbins + bin, &scratch);
+        if (!has_next) break;
+        tm_st16(tm + kColC, w);
+        tm_st16(tm + kColC + 16, w + 16);
+        tm_wait_st();
+        if (n_work != work) {
+            work = n_work; grp = n_grp; bin = (work / a.ngroups) % a.nbins; rec = work / (a.ngroups * a.nbins);
+            spec = reinterpret_cast<const char*>(a.spec) + (size_t)(work / a.ngroups) * spec_stride;
+        }
+        g = n_g;
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -543,6 +583,7 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         a.rec_stride = rec_stride;
         a.prns = p->d_prns;
         a.w32 = p->d_w32;
+        a.nrec = nr;
         a.nprn = p->nprn;
         a.nbins = p->nbins;
         a.ngroups = (p->nprn + GR_ACQ_G - 1) / GR_ACQ_G;
@@ -564,7 +605,8 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         const long long ninv = (long long)nr * p->nbins * a.ngroups;
         if (nfwd > 0x7fffffffLL || ninv > 0x7fffffffLL) { gr_set_error("gr_acq_run_dev: grid too large"); return GR_ERR_ARG; }
         fwd<<<(unsigned)nfwd, GR_FFT_THREADS, GR_FFT_SMEM_BYTES, s>>>(a);
-        inv<<<(unsigned)ninv, GR_FFT_THREADS, GR_ACQ_INV_SMEM, s>>>(a);
+        const long long ninv_grid = ninv < 4LL * gr_lib()->num_sms ? ninv : 4LL * gr_lib()->num_sms;
+        inv<<<(unsigned)ninv_grid, GR_FFT_THREADS, GR_ACQ_INV_SMEM, s>>>(a);
         GR_CUDA(cudaGetLastError());
         p->last_launches += 2;
     }

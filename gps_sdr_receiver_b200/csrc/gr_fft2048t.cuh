@@ -62,11 +62,22 @@ __device__ __forceinline__ void tm_ld_32x32b_x32(uint32_t taddr, float* r) {
 }
 
 // One store/load round on this warp's 32 lanes x 32 columns at `taddr` (lane field = warp's base lane).
+__device__ __forceinline__ void tm_ld_32x32b_x16x2(uint32_t taddr, float* r) {      // two 16-register blocks, one wait
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]),
+          "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]), "=f"(r[17]), "=f"(r[18]),
+          "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]),
+          "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+        : "r"(taddr), "r"(taddr + 16));
+}
 __device__ __forceinline__ void tm_round(uint32_t taddr, float* r) {
     tm_st_16x256b_x4(taddr, r);
     tm_st_16x256b_x4(taddr + (16u << 16), r + 16);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    tm_ld_32x32b_x32(taddr, r);
+    tm_ld_32x32b_x16x2(taddr, r);
 }
 
 // Exchange 2 + stage 3: v[k2] (stage-2 outputs, twiddled) -> v[2 k3 + h] = X[base + 128 (2 k3 + h)]

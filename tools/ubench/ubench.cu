@@ -7,6 +7,7 @@
 #include <vector>
 #include "gr_fft2048.cuh"
 #include "gr_fft2048w.cuh"
+#include "gr_fft2048t.cuh"
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
@@ -179,6 +180,135 @@ __global__ void __launch_bounds__(128) k_tmem(float* out, int iters) {
     if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base_sh), "r"(64));
 }
 
+// ---- 8. ablation of the generation-5 inverse-FFT loop (acq_inv_kernel in gr_acq.cu) ----
+// ABL bits switch pieces OFF: 1 = X stage read + TMA, 2 = c[] fetch + multiply, 4 = twiddles (TMEM loads + cmul),
+// 8 = exchange 2 through TMEM, 16 = exchange 1 (smem + barrier), 32 = |y|^2 accumulation, 64 = butterflies
+__device__ __forceinline__ void u_tm_ld16(uint32_t taddr, float* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+          "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void u_tm_st16(uint32_t taddr, const float* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+        :: "r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),
+           "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]));
+}
+__device__ __forceinline__ void u_tw8(cf* v, int k0, uint32_t taddr) {
+    float w[16];
+    u_tm_ld16(taddr + 2 * k0, w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k0 + k != 0) v[k0 + k] = cmul(v[k0 + k], cf{w[2 * k], w[2 * k + 1]});
+}
+__device__ __forceinline__ void u_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void u_tma(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+
+template <int ABL>
+__global__ void __launch_bounds__(128, 4) k_inv(float* out, const float2* tw1p, const float2* tw2p, const float2* spec, int iters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* buf1 = reinterpret_cast<float4*>(smem_raw);
+    float4* xs = reinterpret_cast<float4*>(smem_raw + 2 * GR_W_BUF1_BYTES);
+    __shared__ __align__(8) uint64_t xbar;
+    __shared__ uint32_t tm_base_sh;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&xbar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (t < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tm_base_sh)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tm = tm_base_sh + ((uint32_t)(32 * (t >> 5)) << 16);
+    {
+        float w[32];
+        for (int i = 0; i < 16; ++i) { const float2 u = tw1p[t * 16 + i]; w[2 * i] = u.x; w[2 * i + 1] = u.y; }
+        u_tm_st16(tm + 96, w); u_tm_st16(tm + 112, w + 16);
+        for (int i = 0; i < 16; ++i) { const float2 u = tw2p[(t & 7) * 16 + i]; w[2 * i] = u.x; w[2 * i + 1] = u.y; }
+        u_tm_st16(tm + 64, w); u_tm_st16(tm + 80, w + 16);
+        u_tm_st16(tm, w); u_tm_st16(tm + 16, w + 16);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    const char* sp = reinterpret_cast<const char*>(spec + (size_t)(blockIdx.x % 64) * 10 * GR_N);
+    if (!(ABL & 1) && t == 0) u_tma(xs, sp, GR_N * 8, &xbar);
+    float acc[16];
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    int par = 0;
+    for (int it = 0; it < iters; ++it) {
+        cf y[16];
+        if (!(ABL & 1)) {
+            u_mbar_wait(&xbar, it & 1);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) { const float4 v = xs[128 * m + t]; y[2 * m] = cf{v.x, v.y}; y[2 * m + 1] = cf{v.z, v.w}; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = cf{acc[j] * 1e-3f + (float)j, acc[(j + 1) & 15] * 1e-3f};
+        }
+        if (!(ABL & 2)) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float w[16];
+                u_tm_ld16(tm + 16 * h, w);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const cf cc = cf{w[2 * j], w[2 * j + 1]}; const cf x = y[8 * h + j];
+                    y[8 * h + j].x = x.x * cc.y + x.y * cc.x; y[8 * h + j].y = x.x * cc.x - x.y * cc.y;
+                }
+            }
+        }
+        if (!(ABL & 64)) dft16(y);
+        if (!(ABL & 4)) { u_tw8(y, 0, tm + 96); u_tw8(y, 8, tm + 96); }
+        if (!(ABL & 16)) {
+            float4* b1 = buf1 + par * (GR_W_BUF1_BYTES / 16);
+            par ^= 1;
+            fftw_ex1_write(b1, t, y);
+            __syncthreads();
+            if (!(ABL & 1) && t == 0 && it + 1 < iters) u_tma(xs, sp + (size_t)((it + 1) % 10) * (GR_N * 8), GR_N * 8, &xbar);
+            fftt_ex1_read(b1, t, y);
+        } else if (!(ABL & 1)) {
+            __syncthreads();
+            if (t == 0 && it + 1 < iters) u_tma(xs, sp + (size_t)((it + 1) % 10) * (GR_N * 8), GR_N * 8, &xbar);
+        }
+        if (!(ABL & 64)) dft16(y);
+        if (!(ABL & 4)) { u_tw8(y, 0, tm + 64); u_tw8(y, 8, tm + 64); }
+        if (!(ABL & 8)) fftt_ex2_stage3(tm + 32, y);
+        else if (!(ABL & 64)) {
+            cf a[8], b[8];
+            for (int i = 0; i < 8; ++i) { a[i] = y[2 * i]; b[i] = y[2 * i + 1]; }
+            dft8(a); dft8(b);
+            for (int i = 0; i < 8; ++i) { y[2 * i] = a[i]; y[2 * i + 1] = b[i]; }
+        }
+        if (!(ABL & 32)) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] += y[j].x * y[j].x + y[j].y * y[j].y;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = y[j].x;
+        }
+    }
+    float s = 0.f;
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 1.2345f) out[0] = s;
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base_sh), "r"(128));
+}
+
 template <typename F>
 static float time_ms(F launch) {
     cudaEvent_t e0, e1;
@@ -227,6 +357,26 @@ int main() {
             rep("exch", 57, time_ms([&] { k_exch<<<grid, 128, GR_W_SMEM_BYTES>>>(d_out, iters); }));
             rep("fftw", 620, time_ms([&] { k_fftw<<<grid, 128, GR_W_SMEM_BYTES>>>(d_out, d_tw, d_tw, iters); }));
         }
+    }
+
+    {   // ablation of the inverse loop at 4 CTAs / SM
+        float2* d_spec; CK(cudaMalloc(&d_spec, (size_t)64 * 10 * 2048 * 8)); CK(cudaMemset(d_spec, 0, (size_t)64 * 10 * 2048 * 8));
+        const int grid = sms * 4, it2 = 2000;
+        auto rep2 = [&](const char* name, float ms) { printf("inv-loop %-28s %.3f ms  cycles/iter/CTA-slot=%.1f\n", name, ms, ms * 1e-3 * ghz * 1e9 / it2 / 4); };
+#define RUN_ABL(M, NAME) { CK(cudaFuncSetAttribute(k_inv<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * GR_W_BUF1_BYTES)); \
+        rep2(NAME, time_ms([&] { k_inv<M><<<grid, 128, 3 * GR_W_BUF1_BYTES>>>(d_out, d_tw, d_tw, d_spec, it2); })); }
+        RUN_ABL(0, "full");
+        RUN_ABL(1, "-X stage/TMA");
+        RUN_ABL(2, "-c fetch+mul");
+        RUN_ABL(4, "-twiddles");
+        RUN_ABL(8, "-exchange2(TMEM)");
+        RUN_ABL(16, "-exchange1(smem+bar)");
+        RUN_ABL(32, "-accumulate");
+        RUN_ABL(1 | 2 | 4, "-X -c -tw");
+        RUN_ABL(8 | 16, "-ex1 -ex2");
+        RUN_ABL(1 | 8 | 16, "-X -ex1 -ex2");
+        RUN_ABL(1 | 2 | 4 | 8 | 16, "math only (dft+acc)");
+        RUN_ABL(64 | 2 | 4 | 32, "data movement only");
     }
     return 0;
 }
