@@ -84,6 +84,7 @@ struct TrackArgs {
     long long rec_stride;   // samples
     long long smp_time;     // SMP_TIME of the first epoch
     int n_epochs, n_active;
+    int stage;              // raw I/Q of each epoch staged in shared memory by TMA (u8 input, 16-byte aligned recordings)
     const int32_t* slots;
     GrChan* state;
     gr_epoch_out* out;
@@ -96,6 +97,7 @@ struct TrackArgs {
 #define GR_TRACK_BUF_BYTES (GR_PART_ROWS * 128 * 16)      // 34816 >= GR_FFT_SMEM_BYTES; FFT buffers alias it
 
 struct TrackSmem {
+    unsigned long long rawbar;           // mbarrier of the raw-sample stage (first member: 8-byte aligned)
     GrChanHot H;                         // this channel's scalar state for the life of the kernel
     float code[GR_N];                    // resampled C/A code of this PRN
     cf rho[16];                          // exp(-i w 128 j / fs)
@@ -117,9 +119,13 @@ struct TrackSmem {
 };
 
 // ---- sample access ------------------------------------------------------------------------------
-template <int IN_FMT>
+// kStage: `base` is the epoch's raw block in shared memory (see track_kernel), else global memory
+template <int IN_FMT, bool kStage>
 __device__ __forceinline__ cf load_raw(const void* base, long long n) {
-    if (IN_FMT == GR_IN_U8IQ) {
+    if (IN_FMT == GR_IN_U8IQ && kStage) {
+        const uchar2 v = reinterpret_cast<const uchar2*>(base)[(int)n];
+        return cf{(float)v.x, (float)v.y};
+    } else if (IN_FMT == GR_IN_U8IQ) {
         const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(base) + n);
         return cf{(float)v.x, (float)v.y};          // integer-valued; affine map applied per sum
     } else {
@@ -237,7 +243,7 @@ __device__ __forceinline__ double fit_code_phase(int mx, double lo, double c, do
 
 // Coherent fold of `nblk` 1-ms blocks starting at block `first` (natural FFT layout):
 //   F[j] = r_t rho_j * sum_b R_b x_b[t + 128 j]
-template <int IN_FMT>
+template <int IN_FMT, bool kStage>
 __device__ __forceinline__ void fold_blocks(cf* F, const void* src, int first, int nblk, cf rt, int t,
                                             const TrackSmem* S) {
     cf A[16];
@@ -250,7 +256,7 @@ __device__ __forceinline__ void fold_blocks(cf* F, const void* src, int first, i
         const long long base = (long long)b * GR_N + t;
         cf x[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = load_raw<IN_FMT>(src, base + 128 * j);
+        for (int j = 0; j < 16; ++j) x[j] = load_raw<IN_FMT, kStage>(src, base + 128 * j);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             A[j].x = fmaf(x[j].x, R.x, A[j].x);
@@ -331,12 +337,37 @@ __device__ __forceinline__ void st_corr_quality(GrChanHot* c, GrChan* g, double 
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
-template <int IN_FMT>
+// mbarrier / TMA helpers of the raw-sample stage
+__device__ __forceinline__ void trk_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+        ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+// one epoch's raw block (bytes, multiple of 16 KiB... of 4 KiB) global -> shared, completion on `bar`
+__device__ __forceinline__ void trk_stage_issue(void* dst, const char* gsrc, unsigned bytes, unsigned long long* bar) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    for (unsigned o = 0; o < bytes; o += 16384u) {
+        const unsigned n = bytes - o < 16384u ? bytes - o : 16384u;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(d + o), "l"(gsrc + o), "r"(n), "r"(b) : "memory");
+    }
+}
+
+// kStage (u8 input only): the epoch's raw block (n_cyc x 4 KiB) is brought into shared memory by TMA while
+// the previous epoch's serial tail (prompt means, edge detector, PLL) runs; both sample passes then read
+// shared memory instead of L2/HBM -- a single recording is a chain of dependent epochs, so load latency,
+// not bandwidth, is what the epoch time is made of.
+template <int IN_FMT, bool kStage>
 __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* fftbuf = reinterpret_cast<cf*>(smem_raw);
     float4* part = reinterpret_cast<float4*>(smem_raw);          // aliases the FFT buffers
     TrackSmem* S = reinterpret_cast<TrackSmem*>(smem_raw + GR_TRACK_BUF_BYTES);
+    unsigned char* stage = smem_raw + GR_TRACK_BUF_BYTES + ((sizeof(TrackSmem) + 15) & ~(size_t)15);
     GrChanHot* C = &S->H;
 
     const int t = threadIdx.x;
@@ -358,14 +389,23 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
         tw2[k] = cf{v.x, v.y};
     }
     for (int i = t; i < GR_N; i += GR_FFT_THREADS) S->code[i] = a.tab.code[(size_t)prn * GR_N + i];
-    if (t == 0) *C = G->h;
+    if (t == 0) {
+        *C = G->h;
+        if (kStage) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&S->rawbar)), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
     __syncthreads();
 
     const long long rec_off = (long long)C->rec * a.rec_stride;
     const char* rec_base = reinterpret_cast<const char*>(a.samples) + rec_off * (IN_FMT == GR_IN_U8IQ ? 2 : 8);
+    const unsigned epoch_bytes = (unsigned)ngps * 2u;
+    if (kStage && t == 0) trk_stage_issue(stage, rec_base, epoch_bytes, &S->rawbar);
 
     for (int e = 0; e < a.n_epochs; ++e) {
-        const void* src = rec_base + (long long)e * ngps * (IN_FMT == GR_IN_U8IQ ? 2 : 8);
+        const void* src = kStage ? (const void*)stage
+                                 : (const void*)(rec_base + (long long)e * ngps * (IN_FMT == GR_IN_U8IQ ? 2 : 8));
         const long long smp_time = a.smp_time + (long long)e * ngps;
         const long long stream_no = smp_time / ngps;
         gr_epoch_out* O = a.out + ((size_t)e * a.n_active + blockIdx.x);
@@ -394,6 +434,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
             O->prn = prn;
         }
         __syncthreads();
+        if (kStage) trk_mbar_wait(&S->rawbar, e & 1);
 
         if (S->branch_sweep) {
             // =============== sweep branch (gpslib.py:1153-1173, 1350-1380) ===============
@@ -407,7 +448,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
                 const cf rt = nco_setup(w32, 0.f, n_cyc, t, S);
                 __syncthreads();
                 cf F[16];
-                fold_blocks<IN_FMT>(F, src, 0, avg, rt, t, S);
+                fold_blocks<IN_FMT, kStage>(F, src, 0, avg, rt, t, S);
                 corr_and_stats(F, cs, 1.0f / ((float)avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
                 z = S->z;
                 if (z > (double)a.cfg.corr_min) {
@@ -419,6 +460,8 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
                 ++j;
                 __syncthreads();                              // S->z / rho / Rm are rewritten next round
             }
+            if (kStage && t == 0 && e + 1 < a.n_epochs)      // all reads of this epoch's block are behind a barrier
+                trk_stage_issue(stage, rec_base + (long long)(e + 1) * epoch_bytes, epoch_bytes, &S->rawbar);
             int running = 1;
             if (delay >= 0) running = 0;
             else if (freq > (double)a.cfg.max_freq) { freq = (double)a.cfg.min_freq; running = 0; }
@@ -453,7 +496,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
             __syncthreads();
             {
                 cf F[16];
-                fold_blocks<IN_FMT>(F, src, (n_cyc - corr_avg) / 2, corr_avg, rt, t, S);
+                fold_blocks<IN_FMT, kStage>(F, src, (n_cyc - corr_avg) / 2, corr_avg, rt, t, S);
                 corr_and_stats(F, cs, 1.0f / ((float)corr_avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
             }
             if (t == 0) {
@@ -511,7 +554,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
                         const bool wrapped = (j + jb) >= 16;
                         const bool valid = vmode == 0 || (vmode == 1 ? wrapped : !wrapped);
                         const long long n = valid ? base + 128 * j : (long long)t;
-                        const cf v = load_raw<IN_FMT>(src, n);
+                        const cf v = load_raw<IN_FMT, kStage>(src, n);
                         x[j].x = valid ? v.x : 0.f;
                         x[j].y = valid ? v.y : 0.f;
                     }
@@ -543,6 +586,8 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
                 }
                 __syncthreads();
             }
+            if (kStage && t == 0 && e + 1 < a.n_epochs)      // the prompt pass was the last reader of this epoch's block
+                trk_stage_issue(stage, rec_base + (long long)(e + 1) * epoch_bytes, epoch_bytes, &S->rawbar);
             // true-sample sums X_k, XB_k (threads 0..n_cyc), then the per-ms means (thread 0)
             if (t <= n_cyc) {
                 const int k = t;
@@ -776,7 +821,8 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
 }
 
 // ---- host API ------------------------------------------------------------------------------------------
-static size_t track_smem_bytes() { return GR_TRACK_BUF_BYTES + sizeof(TrackSmem); }
+static size_t track_smem_bytes() { return GR_TRACK_BUF_BYTES + ((sizeof(TrackSmem) + 15) & ~(size_t)15); }
+static size_t track_stage_bytes(int n_cyc) { return (size_t)n_cyc * GR_N * 2; }
 
 extern "C" int gr_track_default_cfg(gr_track_cfg* cfg) {
     if (!cfg) { gr_set_error("gr_track_default_cfg: null"); return GR_ERR_ARG; }
@@ -814,8 +860,10 @@ extern "C" int gr_track_bank_create(const gr_track_cfg* cfg, gr_track_bank** ban
     GR_CUDA(cudaMemset(b->d_state, 0, sizeof(GrChan) * (size_t)cfg->max_channels));
     GR_CUDA(cudaMalloc((void**)&b->d_slots, sizeof(int32_t) * (size_t)cfg->max_channels));
     GR_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)track_smem_bytes()));
-    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_CF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)track_smem_bytes()));
+    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)track_smem_bytes()));
+    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_CF32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)track_smem_bytes()));
+    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(track_smem_bytes() + track_stage_bytes(GR_MAX_NCYC))));
     *bank = b;
     return GR_OK;
 }
@@ -935,10 +983,14 @@ extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int
     a.out = d_out;
     a.cfg = b->cfg;
     a.tab = gr_lib()->tab;
-    if (b->cfg.in_format == GR_IN_U8IQ)
-        track_kernel<GR_IN_U8IQ><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);
+    // TMA needs 16-byte aligned sources: every recording's first sample, hence base and stride
+    a.stage = b->cfg.in_format == GR_IN_U8IQ && ((uintptr_t)d_samples % 16) == 0 && ((2 * rec_stride) % 16) == 0;
+    if (a.stage)
+        track_kernel<GR_IN_U8IQ, true><<<a.n_active, GR_FFT_THREADS, track_smem_bytes() + track_stage_bytes(b->cfg.n_cyc), s>>>(a);
+    else if (b->cfg.in_format == GR_IN_U8IQ)
+        track_kernel<GR_IN_U8IQ, false><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);
     else
-        track_kernel<GR_IN_CF32><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);
+        track_kernel<GR_IN_CF32, false><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);
     GR_CUDA(cudaGetLastError());
     b->last_stream = s;
     b->last_launches = 1;
