@@ -98,7 +98,7 @@ struct TrackArgs {
 
 struct TrackSmem {
     unsigned long long rawbar;           // mbarrier of the raw-sample stage (first member: 8-byte aligned)
-    GrChanHot H;                         // this channel's scalar state for the life of the kernel
+    GrChan CH;                           // this channel's whole state (scalars + DF / CORRLST rings) for the life of the kernel
     float code[GR_N];                    // resampled C/A code of this PRN
     cf rho[16];                          // exp(-i w 128 j / fs)
     cf Rm[GR_MAX_NCYC + 2];              // Rm[k] = R_{k-1} = exp(-i w (k-1) ms), k = 0..n_cyc
@@ -119,15 +119,20 @@ struct TrackSmem {
 };
 
 // ---- sample access ------------------------------------------------------------------------------
+// u8 -> float without the (quarter-rate) I2F unit: splice the byte into the mantissa of 2^23 and subtract 2^23
+// (exact for 0..255): one PRMT + one FADD per component.
+__device__ __forceinline__ cf u8pair_to_cf(unsigned v16) {
+    const float x = __uint_as_float(__byte_perm(v16, 0x4B000000u, 0x7540)) - 8388608.0f;
+    const float y = __uint_as_float(__byte_perm(v16, 0x4B000000u, 0x7541)) - 8388608.0f;
+    return cf{x, y};          // integer-valued; the affine map x/127.5 - 1 is applied per sum
+}
 // kStage: `base` is the epoch's raw block in shared memory (see track_kernel), else global memory
 template <int IN_FMT, bool kStage>
 __device__ __forceinline__ cf load_raw(const void* base, long long n) {
     if (IN_FMT == GR_IN_U8IQ && kStage) {
-        const uchar2 v = reinterpret_cast<const uchar2*>(base)[(int)n];
-        return cf{(float)v.x, (float)v.y};
+        return u8pair_to_cf(reinterpret_cast<const unsigned short*>(base)[(int)n]);
     } else if (IN_FMT == GR_IN_U8IQ) {
-        const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(base) + n);
-        return cf{(float)v.x, (float)v.y};          // integer-valued; affine map applied per sum
+        return u8pair_to_cf(__ldg(reinterpret_cast<const unsigned short*>(base) + n));
     } else {
         const float2 v = __ldg(reinterpret_cast<const float2*>(base) + n);
         return cf{v.x, v.y};
@@ -368,16 +373,17 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
     float4* part = reinterpret_cast<float4*>(smem_raw);          // aliases the FFT buffers
     TrackSmem* S = reinterpret_cast<TrackSmem*>(smem_raw + GR_TRACK_BUF_BYTES);
     unsigned char* stage = smem_raw + GR_TRACK_BUF_BYTES + ((sizeof(TrackSmem) + 15) & ~(size_t)15);
-    GrChanHot* C = &S->H;
+    GrChanHot* C = &S->CH.h;
 
     const int t = threadIdx.x;
     const int slot = a.slots[blockIdx.x];
-    GrChan* G = a.state + slot;
+    GrChan* Gg = a.state + slot;        // global copy: read once, written back at the end
+    GrChan* G = &S->CH;                 // rings are touched every epoch: keep them out of L2 latency
     const int n_cyc = a.cfg.n_cyc;
     const int ngps = n_cyc * GR_N;
     const int no_sec = 1024 / n_cyc;
     const int corr_avg = a.cfg.corr_avg < n_cyc ? a.cfg.corr_avg : n_cyc;
-    const int prn = G->h.prn;
+    const int prn = Gg->h.prn;
     const float2* cs = a.tab.conjspec + (size_t)prn * GR_N;
 
     cf tw1[16], tw2[16];
@@ -389,8 +395,9 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
         tw2[k] = cf{v.x, v.y};
     }
     for (int i = t; i < GR_N; i += GR_FFT_THREADS) S->code[i] = a.tab.code[(size_t)prn * GR_N + i];
+    for (int i = t; i < (int)(sizeof(GrChan) / 4); i += GR_FFT_THREADS)
+        reinterpret_cast<uint32_t*>(G)[i] = reinterpret_cast<const uint32_t*>(Gg)[i];
     if (t == 0) {
-        *C = G->h;
         if (kStage) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&S->rawbar)), "r"(1));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -817,7 +824,9 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
         }
         __syncthreads();
     }
-    if (t == 0) G->h = *C;
+    __syncthreads();
+    for (int i = t; i < (int)(sizeof(GrChan) / 4); i += GR_FFT_THREADS)
+        reinterpret_cast<uint32_t*>(Gg)[i] = reinterpret_cast<const uint32_t*>(G)[i];
 }
 
 // ---- host API ------------------------------------------------------------------------------------------

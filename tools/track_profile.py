@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Short single-recording tracking run (BASELINE configs[2] shape) for ncu: 12 channels, N_CYC = 8."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import bench
+from gps_sdr_receiver_b200 import _capi, synth
+from gps_sdr_receiver_b200.tracking import TrackBank
+from gps_sdr_receiver_b200._capi import EPOCH_OUT
+
+n_ep = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
+_capi.init(0)
+tsats = bench.track_sats(7)
+ngps = 8 * 2048
+rec = synth.make_iq_dev(tsats, n_ep * 8, noise_sigma=0.25, seed=77, device=0)
+out = torch.empty((n_ep, 12, EPOCH_OUT.itemsize), dtype=torch.uint8, device="cuda")
+bank = TrackBank(8, 16, device=0)
+for s in tsats:
+    bank.add(s.prn, 50.0 * np.round(s.doppler / 50.0), (int(s.delay) + 1) % 2048)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+bank.process_dev(rec, ngps, n_ep, out=out)
+e1.record()
+torch.cuda.synchronize()
+print("us per epoch", e0.elapsed_time(e1) * 1e3 / n_ep)
