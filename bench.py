@@ -269,7 +269,7 @@ def run_b200(args):
     ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     value = world * R * CELLS_PER_REC / (ms_step * 1e-3)
 
-    # dominant kernel alone (acq_kernel), CUDA events on its stream
+    # the two grid kernels alone (acq_fwd_kernel 4 % + acq_inv_kernel 96 %), CUDA events on their stream
     barrier()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_a = time.perf_counter()
@@ -301,7 +301,7 @@ def run_b200(args):
     t_e2e = max_over_ranks(t_e2e)
     e2e_value = world * R * CELLS_PER_REC * args.steps / t_e2e
     assert np.array_equal(best_np["bin"], AcqPlan.best_from_tensor(plan.search_dev(bufs[(args.steps - 1) % 2], nrec=R))["bin"])
-    launches = args.steps * 2
+    launches = args.steps * 3          # acq_fwd_kernel, acq_inv_kernel, acq_best_kernel per step
     del bufs, cells_dev, host_in
 
     line = {
@@ -316,7 +316,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": R * REC_SAMPLES * 2,
                 "d2h_bytes_per_step": R * NPRN * ACQ_BEST.itemsize, "api": "AcqPlan.search -> gr_acq_search_host (C ABI), pinned host buffers"},
         "gpu_launches": launches,
-        "roofline": {"bound": "fp32", "kernel": "acq_kernel", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+        "roofline": {"bound": "fp32", "kernel": "acq_inv_kernel (+ acq_fwd_kernel, 4 % of the launch pair)", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp32_peak, "traffic": None,
                      "peak_source": f"measured in this run: register-resident FFMA chains on all SMs (gr_debug_fp32_peak); "
                                     f"theoretical at 1965 MHz = {FP32_PEAK_THEORY:.1f}",
@@ -411,6 +411,58 @@ def run_b200(args):
         line["gpu_launches"] = launches
         del rec, out_dev, host_rec, host_out
 
+        # ---- tracking, many recordings per launch (the per-GPU share of configs[4]: independent recordings) ----
+        if args.batch_recs > 0:
+            RB, secs = args.batch_recs, args.batch_seconds
+            nb_ep = int(secs * 1000) // TRACK_NCYC
+            span = nb_ep * ngps
+            brec = torch.empty(2 * RB * span, dtype=torch.uint8, device=dev)
+            for r in range(RB):
+                for s0 in range(0, span, piece):
+                    n = min(piece, span - s0)
+                    synth.make_iq_dev(tsats, n // 2048, noise_sigma=0.25, seed=500 + r + 100 * rank, start_sample=s0,
+                                      out=brec[2 * (r * span + s0):2 * (r * span + s0 + n)], device=local)
+            bout = torch.empty((nb_ep, RB * TRACK_NCH, EPOCH_OUT.itemsize), dtype=torch.uint8, device=dev)
+
+            def new_batch_bank():
+                bank = TrackBank(TRACK_NCYC, RB * TRACK_NCH, device=local)
+                for r in range(RB):
+                    for s in tsats:
+                        bank.add(s.prn, 50.0 * np.round(s.doppler / 50.0), (int(s.delay) + 1) % 2048, rec=r)
+                return bank
+
+            wb = new_batch_bank()
+            wb.process_dev(brec, ngps, min(nb_ep, 200), rec_stride=span, out=bout[:min(nb_ep, 200)])
+            wb.close()
+            bank = new_batch_bank()
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_a = time.perf_counter()
+            b0.record()
+            bank.process_dev(brec, ngps, nb_ep, rec_stride=span, out=bout)
+            b1.record()
+            barrier()
+            windows.append((t_a, time.perf_counter()))
+            t_batch = max_over_ranks(b0.elapsed_time(b1)) * 1e-3
+            last = TrackBank.records_from_tensor(bout[nb_ep - 1:nb_ep])[0]
+            assert int((last["locked"] == 1).sum()) == RB * TRACK_NCH, "a batched channel lost lock"
+            bank.close()
+            b_raw = 2 * RB * span
+            b_out = nb_ep * RB * TRACK_NCH * EPOCH_OUT.itemsize
+            line["tracking_batch"] = {
+                "metric": "tracking x-realtime, aggregate over independent recordings", "value": world * RB * secs / t_batch,
+                "unit": "x-realtime", "seconds": t_batch,
+                "config": {"workload": f"{RB} recordings x {TRACK_NCH} channels per GPU, {secs:.0f} s each, 8-ms epochs, one launch "
+                                       f"({RB * TRACK_NCH} channel CTAs; per-GPU share of BASELINE configs[4])"},
+                "roofline": {"bound": "hbm", "kernel": "track_kernel", "achieved": (b_raw + b_out) / t_batch / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": (b_raw + b_out) / t_batch / 1e9 / hbm_peak, "traffic": None,
+                             "fp32_achieved_tflops": nb_ep * RB * TRACK_NCH * flop_ce / t_batch / 1e12, "fp32_peak_tflops": fp32_peak,
+                             "note": "algorithmic bytes = each recording's raw I/Q once + one record per channel-epoch; the kernel is "
+                                     "FP32/latency-bound (about 260 flop per byte, DESIGN.md 4.3), so the HBM fraction stays small by construction"},
+            }
+            line["gpu_launches"] += 1
+            del brec, bout
+
     clocks.stop()
     line["clocks"] = clocks.summary(windows)
 
@@ -436,6 +488,8 @@ def main():
     ap.add_argument("--recs", type=int, default=512, help="independent 10-ms recordings per GPU per step")
     ap.add_argument("--track-seconds", type=float, default=600.0)
     ap.add_argument("--track-reps", type=int, default=2)
+    ap.add_argument("--batch-recs", type=int, default=24, help="recordings per GPU in the batched tracking line (0 = skip)")
+    ap.add_argument("--batch-seconds", type=float, default=60.0)
     ap.add_argument("--skip-tracking", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
