@@ -147,6 +147,19 @@ def test_full_size_cold_start_grid_properties(gpu):
     _check_cells(sub, ref)
 
 
+def test_weak_signal_fine_grid_vs_oracle(gpu, scen32):
+    """BASELINE config 4 shape in small: 10 ms coherent x 3 non-coherent, 50 Hz Doppler bins, |.|^2; a PRN
+    group that is not full (3 PRNs) and more bins than one forward CTA chunk."""
+    from gps_sdr_receiver_b200.acquisition import AcqPlan, GR_ACQ_POW
+    prns = [int(p) for p in scen32.gold["grid_prns"]][:3]
+    bins = [-150.0 + 50.0 * b for b in range(7)]
+    n_ms = 10 * 3
+    plan = AcqPlan(prns, bins, 10, 3, GR_ACQ_POW)
+    cells = plan.run(scen32.raw[:2 * n_ms * 2048])[0]
+    ref = orc.acq_grid(orc.raw_to_complex(scen32.raw[:2 * n_ms * 2048]), prns, bins[0], 50.0, len(bins), 10, 3, orc.ACQ_MODE_POW)
+    _check_cells(cells, ref)
+
+
 def test_ragged_and_invalid_inputs(gpu):
     from gps_sdr_receiver_b200 import _capi
     from gps_sdr_receiver_b200.acquisition import AcqPlan
