@@ -29,8 +29,9 @@ EPOCH_OUT = np.dtype([
     ("code_phase", "<f8"), ("max_corr", "<f8"), ("corr_q", "<f8"), ("corr_l", "<f8"), ("freq", "<f8"),
     ("report_freq", "<f8"), ("phase", "<f8"), ("amplitude", "<f4"), ("std_dev", "<f4"), ("corr3", "<f4", (3,)),
     ("corr_mean", "<f4"), ("corr_std", "<f4"), ("erased", "<i4"),
-    ("prompt", "<f4", (2 * GR_MAX_PROMPT,)),
+    ("prompt", "<f4", (2 * GR_MAX_PROMPT,)), ("reserved", "<i4", (2,)),
 ], align=True)
+assert EPOCH_OUT.itemsize == 448
 
 
 ACQ_BEST = np.dtype([("prn", "<i4"), ("bin", "<i4"), ("cell", ACQ_CELL)])

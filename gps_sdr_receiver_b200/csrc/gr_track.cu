@@ -84,6 +84,7 @@ struct TrackArgs {
     long long rec_stride;   // samples
     long long smp_time;     // SMP_TIME of the first epoch
     int n_epochs, n_active;
+    int out_tma;            // records leave by cp.async.bulk (16-byte aligned output array)
     int stage;              // raw I/Q of each epoch staged in shared memory by TMA (u8 input, 16-byte aligned recordings)
     const int32_t* slots;
     GrChan* state;
@@ -97,6 +98,7 @@ struct TrackArgs {
 #define GR_TRACK_BUF_BYTES (GR_PART_ROWS * 128 * 16)      // 34816 >= GR_FFT_SMEM_BYTES; FFT buffers alias it
 
 struct TrackSmem {
+    gr_epoch_out out[2];                 // the epoch's record is assembled here (448 B each, 16-byte aligned) and leaves by TMA
     unsigned long long rawbar;           // mbarrier of the raw-sample stage (first member: 8-byte aligned)
     GrChan CH;                           // this channel's whole state (scalars + DF / CORRLST rings) for the life of the kernel
     float code[GR_N];                    // resampled C/A code of this PRN
@@ -415,7 +417,9 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
                                  : (const void*)(rec_base + (long long)e * ngps * (IN_FMT == GR_IN_U8IQ ? 2 : 8));
         const long long smp_time = a.smp_time + (long long)e * ngps;
         const long long stream_no = smp_time / ngps;
-        gr_epoch_out* O = a.out + ((size_t)e * a.n_active + blockIdx.x);
+        gr_epoch_out* gO = a.out + ((size_t)e * a.n_active + blockIdx.x);
+        gr_epoch_out* O = &S->out[e & 1];       // assembled in shared memory: no global store sits in front of a barrier
+        if (t == 0 && a.out_tma) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // record e-2 has left
         const bool report = (stream_no % no_sec) == 0;
 
         // ---- epoch prologue (gpslib.py:1142-1151) ----
@@ -821,9 +825,22 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
             O->phase = (double)C->phase;
             O->amplitude = C->amplitude;
             O->std_dev = (float)C->std_dev;
+            O->reserved[0] = 0; O->reserved[1] = 0;
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the record was written through the generic proxy
         __syncthreads();
+        if (a.out_tma) {
+            if (t == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(gO), "r"((unsigned)__cvta_generic_to_shared(O)), "r"((unsigned)sizeof(gr_epoch_out)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            for (int i = t; i < (int)(sizeof(gr_epoch_out) / 4); i += GR_FFT_THREADS)
+                reinterpret_cast<uint32_t*>(gO)[i] = reinterpret_cast<const uint32_t*>(O)[i];
+        }
     }
+    if (t == 0 && a.out_tma) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncthreads();
     for (int i = t; i < (int)(sizeof(GrChan) / 4); i += GR_FFT_THREADS)
         reinterpret_cast<uint32_t*>(Gg)[i] = reinterpret_cast<const uint32_t*>(G)[i];
@@ -993,6 +1010,7 @@ extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int
     a.cfg = b->cfg;
     a.tab = gr_lib()->tab;
     // TMA needs 16-byte aligned sources: every recording's first sample, hence base and stride
+    a.out_tma = ((uintptr_t)d_out % 16) == 0;
     a.stage = b->cfg.in_format == GR_IN_U8IQ && ((uintptr_t)d_samples % 16) == 0 && ((2 * rec_stride) % 16) == 0;
     if (a.stage)
         track_kernel<GR_IN_U8IQ, true><<<a.n_active, GR_FFT_THREADS, track_smem_bytes() + track_stage_bytes(b->cfg.n_cyc), s>>>(a);

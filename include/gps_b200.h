@@ -121,7 +121,8 @@ typedef struct gr_track_cfg {      /* gpsglob.py:38-42, 63-75, 119-125          
 
 /* Per channel and epoch: everything SatStream.process leaves behind that a caller can
  * observe (gpslib.py:1141-1210).  Doubles where the reference holds python floats /
- * float64, floats where it holds float32.  440 bytes. */
+ * float64, floats where it holds float32.  448 bytes (a multiple of 16: the kernel
+ * stores records with one TMA bulk copy each). */
 typedef struct gr_epoch_out {
     int32_t prn;
     int32_t sweep;            /* SWEEP after this epoch                                  */
@@ -155,6 +156,7 @@ typedef struct gr_epoch_out {
     int32_t erased;           /* bit 0: EDGES/PREV_SAMPLES erased before this epoch (stream  */
                               /* gap or sweep request), bit 1: initSweep ran at its end   */
     float prompt[2 * GR_MAX_PROMPT];   /* gpsData re,im (complex64)                      */
+    int32_t reserved[2];               /* pads the record to 448 bytes                   */
 } gr_epoch_out;
 
 int gr_track_default_cfg(gr_track_cfg* cfg);

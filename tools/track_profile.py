@@ -11,17 +11,20 @@ from gps_sdr_receiver_b200.tracking import TrackBank
 from gps_sdr_receiver_b200._capi import EPOCH_OUT
 
 n_ep = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
+n_rec = int(sys.argv[2]) if len(sys.argv) > 2 else 1          # recordings (aliasing the same samples)
 _capi.init(0)
 tsats = bench.track_sats(7)
 ngps = 8 * 2048
 rec = synth.make_iq_dev(tsats, n_ep * 8, noise_sigma=0.25, seed=77, device=0)
-out = torch.empty((n_ep, 12, EPOCH_OUT.itemsize), dtype=torch.uint8, device="cuda")
-bank = TrackBank(8, 16, device=0)
-for s in tsats:
-    bank.add(s.prn, 50.0 * np.round(s.doppler / 50.0), (int(s.delay) + 1) % 2048)
+out = torch.empty((n_ep, 12 * n_rec, EPOCH_OUT.itemsize), dtype=torch.uint8, device="cuda")
+bank = TrackBank(8, 12 * n_rec, device=0)
+for r in range(n_rec):
+    for s in tsats:
+        bank.add(s.prn, 50.0 * np.round(s.doppler / 50.0), (int(s.delay) + 1) % 2048, rec=r)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-bank.process_dev(rec, ngps, n_ep, out=out)
+bank.process_dev(rec, ngps, n_ep, rec_stride=0, out=out)
 e1.record()
 torch.cuda.synchronize()
-print("us per epoch", e0.elapsed_time(e1) * 1e3 / n_ep)
+print(n_rec, "recordings: us per epoch", e0.elapsed_time(e1) * 1e3 / n_ep)
+bank.close()
