@@ -60,6 +60,12 @@ def _worker_body(rank, world, port, q):
     mb = multi.partition(len(BINS), world, rank)
     shard = _oracle_best(recs[0], PRNS, [BINS[b] for b in mb])
     merged = multi.gather_bin_shards(shard, len(BINS))
+    # (3) per-stream results of a batch (configs[4]): ragged per-rank arrays, rank 1 empty on purpose
+    from gps_sdr_receiver_b200.batch import STREAM_RESULT, gather_stream_results
+    mine_sr = np.zeros(3 if rank == 0 else 0, dtype=STREAM_RESULT)
+    mine_sr["rec"], mine_sr["prn"], mine_sr["freq"] = rank, np.arange(mine_sr.size) + 1, 1000.5 * (rank + 1)
+    allsr = gather_stream_results(mine_sr)
+    assert allsr.size == 3 and list(allsr["prn"]) == [1, 2, 3] and set(allsr["rec"]) == {0} and allsr["freq"][0] == 1000.5
     q.put((rank, allrec.tobytes(), merged.tobytes()))
     dist.barrier()
     dist.destroy_process_group()
