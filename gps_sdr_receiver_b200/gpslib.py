@@ -10,6 +10,7 @@ from __future__ import annotations
 
 from .tables import GPSCacode, chips, code_spectrum          # noqa: F401
 from .tracking import SatStream, TrackBank                   # noqa: F401
+from .navbits import FrameDecoder                            # noqa: F401  (evalEdges .. Subframe, gpslib.py:1451-1580)
 
 import numpy as _np
 

@@ -60,7 +60,8 @@ class Sat:
     doppler_rate: float = 0.0  # Hz/s
     bit_offset_ms: int = 7    # first nav-bit boundary (ms since start)
     bit_seed: int = 0         # seed of the nav-bit stream
-    bits: np.ndarray | None = field(default=None, repr=False)  # optional +-1 bits
+    bits: np.ndarray | None = field(default=None, repr=False)  # optional +-1 bits, indexed by the ABSOLUTE bit number
+                                                               # (modulo their length): e.g. 2 * navbits.encode_frames(..) - 1
 
 
 def _nav_bits(sat: Sat, nbits: int) -> np.ndarray:
@@ -89,9 +90,12 @@ def make_iq(sats: list[Sat], n_ms: int, noise_sigma: float = 0.25, seed: int = 1
         # nav bits: 20 ms per bit, boundaries aligned with code starts
         code_no = np.floor((idx.astype(np.float64) - s.delay) / CODE_SAMPLES).astype(np.int64)
         bit_no = np.floor_divide(code_no - s.bit_offset_ms, 20)
-        nb = int(bit_no.max() - bit_no.min()) + 1
-        bits = _nav_bits(s, nb + 4)
-        nav = bits[bit_no - bit_no.min()].astype(np.float64)
+        if s.bits is not None:               # explicit message: consistent when a recording is generated in pieces
+            nav = np.asarray(s.bits, dtype=np.float64)[np.mod(bit_no, len(s.bits))]
+        else:
+            nb = int(bit_no.max() - bit_no.min()) + 1
+            bits = _nav_bits(s, nb + 4)
+            nav = bits[bit_no - bit_no.min()].astype(np.float64)
         phase = 2.0 * np.pi * (s.doppler * tt + 0.5 * s.doppler_rate * tt * tt) + s.phi0
         x += s.amp * code * nav * np.exp(1j * phase)
     rng = np.random.default_rng(seed + 31 * (start_sample // CODE_SAMPLES))
