@@ -43,6 +43,11 @@ class SynthSat(C.Structure):
                 ("doppler", C.c_double), ("doppler_rate", C.c_double), ("delay", C.c_double), ("phi0", C.c_double)]
 
 
+class SynthGeoSat(C.Structure):
+    _fields_ = [("prn", C.c_int32), ("n_nodes", C.c_int32), ("n_bits", C.c_int32), ("amp", C.c_float),
+                ("bit_t0_ms", C.c_int64), ("d_tau", C.c_void_p), ("d_bits", C.c_void_p)]
+
+
 class TrackCfg(C.Structure):
     _fields_ = [("n_cyc", C.c_int32), ("corr_avg", C.c_int32), ("sweep_corr_avg", C.c_int32),
                 ("it_sweep", C.c_int32), ("corr_min", C.c_float), ("min_freq", C.c_float),
@@ -74,6 +79,8 @@ SIGNATURES = {
     "gr_acq_search_dev": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P]),
     "gr_acq_search_host": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P]),
     "gr_synth_iq_dev": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, C.c_float, C.c_uint64, _P]),
+    "gr_synth_geo_dev": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, C.c_int64, C.c_double, C.c_double, C.c_float,
+                                   C.c_uint64, _P]),
     "gr_debug_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "gr_track_default_cfg": (C.c_int, [C.POINTER(TrackCfg)]),
     "gr_track_bank_create": (C.c_int, [C.POINTER(TrackCfg), C.POINTER(_P)]),

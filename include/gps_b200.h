@@ -195,6 +195,22 @@ typedef struct gr_synth_sat {
 int gr_synth_iq_dev(uint8_t* d_out, int64_t nsamples, int64_t start_sample, const gr_synth_sat* sats,
                     int nsat, float noise_sigma, uint64_t seed, void* stream);
 
+/* Geometry-consistent variant: every satellite's signal is a function of its own clock
+ * reading t_sat = t_rx - tau(t_rx), tau given at nodes `node_dt` seconds apart (node 0 one step before sample 0,
+ * 4-point Lagrange interpolation): code phase = t_sat mod 1 ms, nav bit = bits[floor((t_sat - bit_t0) / 20 ms)],
+ * carrier phase = -2 pi f_L1 tau.  t_rx = t0_ms * 1e-3 + t0_frac + n / fs is the receiver clock reading. */
+typedef struct gr_synth_geo_sat {
+    int32_t prn;
+    int32_t n_nodes;
+    int32_t n_bits;
+    float amp;
+    int64_t bit_t0_ms;       /* satellite-clock time of bits[0], ms                                */
+    const double* d_tau;     /* device pointer: n_nodes values of (receiver clock - satellite clock), s */
+    const int8_t* d_bits;    /* device pointer: n_bits nav bits, 0 / 1                             */
+} gr_synth_geo_sat;
+int gr_synth_geo_dev(uint8_t* d_out, int64_t nsamples, int64_t start_sample, const gr_synth_geo_sat* sats, int nsat,
+                     int64_t t0_ms, double t0_frac, double node_dt, float noise_sigma, uint64_t seed, void* stream);
+
 /* ---- debug / test hooks ----------------------------------------------------------------- */
 /* forward (inverse=0) or unnormalised inverse FFT-2048 of `batch` vectors, complex64 */
 int gr_debug_fft2048(const float* h_in, float* h_out, int batch, int inverse);
