@@ -120,3 +120,40 @@ def make_iq_dev(sats: list[GeoSat], n_ms: int, tow0: float, rx_clock_bias: float
                                              float(noise_sigma), int(seed), st))
     torch.cuda.synchronize()
     return out
+
+
+def make_iq_host(sats: list[GeoSat], n_ms: int, tow0: float, rx_clock_bias: float, noise_sigma: float = 0.25, seed: int = 1,
+                 piece_ms: int = 250) -> np.ndarray:
+    """numpy twin of make_iq_dev (same signal model, float64 math, numpy noise): slow (about 5 s of CPU per second
+    of recording and satellite); for CPU-only experiments such as oracle/e2e_reference_fix.py."""
+    from .synth import gold_chips
+    out = np.empty(2 * n_ms * 2048, dtype=np.uint8)
+    t0 = tow0 + rx_clock_bias
+    t0_ms = int(math.floor(t0 * 1000.0))
+    t0_frac = t0 - t0_ms * 1e-3
+    chips = {s.prn: gold_chips(s.prn).astype(np.float64) for s in sats}
+    rng = np.random.default_rng(seed)
+    for m0 in range(0, n_ms, piece_ms):
+        m1 = min(n_ms, m0 + piece_ms)
+        n = np.arange(m0 * 2048, m1 * 2048, dtype=np.int64)
+        trel = n.astype(np.float64) / 2048000.0
+        x = trel / NODE_DT + 1.0
+        sig = np.zeros(n.size, dtype=np.complex128)
+        for s in sats:
+            k = np.clip(np.floor(x).astype(np.int64), 1, len(s.tau) - 3)
+            u = x - k
+            y0, y1, y2, y3 = s.tau[k - 1], s.tau[k], s.tau[k + 1], s.tau[k + 2]
+            tau = (-u * (u - 1) * (u - 2) / 6 * y0 + (u + 1) * (u - 1) * (u - 2) / 2 * y1
+                   - (u + 1) * u * (u - 2) / 2 * y2 + (u + 1) * u * (u - 1) / 6 * y3)
+            ysat = (t0_frac + (trel - tau)) * 1e3
+            ms_f = np.floor(ysat)
+            ci = np.minimum((ysat - ms_f) * 1023.0, 1022.999).astype(np.int64)
+            b = np.floor_divide(t0_ms + ms_f.astype(np.int64) - int(round(s.bit_t0 * 1000)), 20)
+            nav = 2.0 * s.bits[np.clip(b, 0, len(s.bits) - 1)].astype(np.float64) - 1.0
+            cyc = -F_L1 * tau
+            sig += s.amp * chips[s.prn][ci] * nav * np.exp(2j * np.pi * (cyc - np.floor(cyc)))
+        sig += noise_sigma * (rng.standard_normal(n.size) + 1j * rng.standard_normal(n.size))
+        q = np.empty(2 * n.size)
+        q[0::2], q[1::2] = sig.real, sig.imag
+        out[2 * m0 * 2048:2 * m1 * 2048] = np.clip(np.rint((q + 1.0) * 127.5), 0, 255).astype(np.uint8)
+    return out
