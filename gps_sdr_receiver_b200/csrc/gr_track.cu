@@ -615,36 +615,43 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
                 S->xs[k] = make_float4(X.x, X.y, XB.x, XB.y);
             }
             __syncthreads();
+            // seg_m = X_m - XB_m + XB_{m+1} (m < n_cyc), tail = X_n - XB_n; one segment per thread (the FP64
+            // divisions run in parallel), prompt index = (first segment present ? 1 : 0) + m - 1
+            const int nps0 = C->carry_cnt;
+            const bool first_present = nps0 + d > 0;
+            const int np_total = (first_present ? 1 : 0) + (n_cyc - 1) + (d == 0 ? 1 : 0);
+            double tail_re = 0.0, tail_im = 0.0;
+            if (t <= n_cyc) {
+                const int m = t;
+                const float4 v = S->xs[m];
+                double sre = (double)v.x - (double)v.z, sim = (double)v.y - (double)v.w;
+                if (m < n_cyc) { const float4 u = S->xs[m + 1]; sre += (double)u.z; sim += (double)u.w; }
+                if (m == 0) {
+                    if (first_present) {
+                        const int cnt = nps0 + d;
+                        S->pr_re[0] = (C->carry_re + sre) / (double)cnt;
+                        S->pr_im[0] = (C->carry_im + sim) / (double)cnt;
+                    }
+                } else if (m < n_cyc || d == 0) {
+                    const int idx = (first_present ? 1 : 0) + m - 1;
+                    S->pr_re[idx] = sre / (double)GR_N;
+                    S->pr_im[idx] = sim / (double)GR_N;
+                } else {
+                    tail_re = sre;
+                    tail_im = sim;
+                }
+            }
+            __syncthreads();
+            if (t == n_cyc) {                                  // carry-over of the partial code period (gpslib.py:1440-1441)
+                if (d == 0) { C->carry_cnt = 0; C->carry_re = 0.0; C->carry_im = 0.0; }
+                else { C->carry_cnt = GR_N - d; C->carry_re = tail_re; C->carry_im = tail_im; }
+            }
             if (t == 0) {
-                // seg_m = X_m - XB_m + XB_{m+1} (m < n_cyc), tail = X_n - XB_n
-                const int nps = C->carry_cnt;
+                const int nps = nps0;
                 int n1 = nps + d;
                 long long st;
                 if (n1 == 0) { n1 = GR_N; st = smp_time; } else { st = smp_time + d - GR_N; }
-                int np = 0;
-                const double cre = C->carry_re, cim = C->carry_im;
-                for (int m = 0; m <= n_cyc; ++m) {
-                    const float4 v = S->xs[m];
-                    double sre = (double)v.x - (double)v.z, sim = (double)v.y - (double)v.w;
-                    if (m < n_cyc) { const float4 u = S->xs[m + 1]; sre += (double)u.z; sim += (double)u.w; }
-                    if (m == 0) {
-                        const int cnt = nps + d;
-                        if (cnt > 0) {
-                            S->pr_re[np] = (cre + sre) / (double)cnt;
-                            S->pr_im[np] = (cim + sim) / (double)cnt;
-                            ++np;
-                        }
-                    } else if (m < n_cyc || d == 0) {
-                        S->pr_re[np] = sre / (double)GR_N;
-                        S->pr_im[np] = sim / (double)GR_N;
-                        ++np;
-                        if (m == n_cyc) { C->carry_cnt = 0; C->carry_re = 0.0; C->carry_im = 0.0; }
-                    } else {
-                        C->carry_cnt = GR_N - d;
-                        C->carry_re = sre;
-                        C->carry_im = sim;
-                    }
-                }
+                const int np = np_total;
                 S->n_prompt = np;
                 // ---- edge detector (gpslib.py:1417-1436), threshold from the PREVIOUS epoch's STD_DEV ----
                 unsigned long long mask = 0ull;
