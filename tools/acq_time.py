@@ -1,24 +1,27 @@
 #!/usr/bin/env python
-"""Development harness: time the inverse-FFT acquisition kernel variants (GPSB200_ACQ_VARIANT) on the
-config-2 grid and check every variant's cells against variant 0.
+"""Development harness: time the acquisition kernel pair on the config-2 grid and (optionally) compare the cells
+with a saved run -- the check used while the inverse kernel went through its generations (all of which were
+bit-identical to the first):
 
-    python tools/acq_variants.py 0 0x41 0x43 ...        # driver: one subprocess per variant
+    python tools/acq_time.py [recs] [steps] [--save ref.npy | --compare ref.npy]
 """
 import json
 import os
-import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def one(variant: str, recs: int, steps: int):
+def main():
     import numpy as np
     import torch
     import bench
     from gps_sdr_receiver_b200 import _capi, synth
     from gps_sdr_receiver_b200.acquisition import AcqPlan, GR_ACQ_POW
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    recs = int(args[0]) if args else 256
+    steps = int(args[1]) if len(args) > 1 else 5
     _capi.init(0)
     sats = bench.bench_sats(11)
     bufs = [synth.make_iq_dev(sats, recs * 10, noise_sigma=0.25, seed=i, device=0) for i in range(4)]
@@ -37,14 +40,12 @@ def one(variant: str, recs: int, steps: int):
     plan.run_dev(bufs[0], nrec=recs, out=out)
     torch.cuda.synchronize()
     cells = AcqPlan.cells_from_tensor(out).copy()
-    ref_path = os.path.join(ROOT, "gpurun_out", "variant0_cells.npy")
-    res = {"variant": variant, "ms": ms, "cells_per_s": recs * bench.CELLS_PER_REC / (ms * 1e-3),
+    res = {"recordings": recs, "ms": ms, "cells_per_s": recs * bench.CELLS_PER_REC / (ms * 1e-3),
            "tflops": recs * bench.FLOP_PER_REC / (ms * 1e-3) / 1e12}
-    if int(variant, 0) == 0:
-        os.makedirs(os.path.dirname(ref_path), exist_ok=True)
-        np.save(ref_path, cells)
-    elif os.path.exists(ref_path):
-        ref = np.load(ref_path)
+    if "--save" in sys.argv:
+        np.save(sys.argv[sys.argv.index("--save") + 1], cells)
+    if "--compare" in sys.argv:
+        ref = np.load(sys.argv[sys.argv.index("--compare") + 1])
         res["mx_equal"] = bool(np.array_equal(ref["mx"], cells["mx"]))
         res["max_rel_peak"] = float(np.max(np.abs(ref["peak"] - cells["peak"]) / ref["peak"]))
         res["bitwise_equal"] = bool(ref.tobytes() == cells.tobytes())
@@ -52,13 +53,4 @@ def one(variant: str, recs: int, steps: int):
 
 
 if __name__ == "__main__":
-    if sys.argv[1] == "--one":
-        one(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]))
-    else:
-        recs = int(os.environ.get("RECS", "256"))
-        steps = int(os.environ.get("STEPS", "5"))
-        for v in sys.argv[1:]:
-            env = dict(os.environ, GPSB200_ACQ_VARIANT=str(int(v, 0)))
-            r = subprocess.run([sys.executable, __file__, "--one", v, str(recs), str(steps)], env=env, capture_output=True, text=True,
-                               timeout=300)
-            print(r.stdout.strip() or ("FAILED " + v + ": " + r.stderr[-800:]), flush=True)
+    main()
