@@ -815,26 +815,33 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
                 }
             }
         }
-        __syncthreads();
+        // no barrier here: everything below was produced by thread 0 itself (the loop filter / sweep bookkeeping above)
         if (t == 0) {
-            O->sweep = C->sweep;
-            O->delay = C->delay;
-            O->locked = C->locked;
-            O->ms_time = C->ms_time;
-            O->n_prev = C->carry_cnt;
-            O->max_corr = C->max_corr;
-            O->corr_q = C->corr_q;
-            O->corr_l = C->corr_l;
-            O->freq = C->freq;
-            O->freq_weak = C->freq_weak;
-            O->edge0 = C->edge0;
-            O->edge_len = C->edge_len;
-            O->phase = (double)C->phase;
-            O->amplitude = C->amplitude;
-            O->std_dev = (float)C->std_dev;
+            // all loads first: C and O are both shared memory, the compiler will not reorder loads over stores
+            const int v_sweep = C->sweep, v_delay = C->delay, v_locked = C->locked, v_ms = C->ms_time, v_prev = C->carry_cnt;
+            const int v_weak = C->freq_weak, v_e0 = C->edge0, v_el = C->edge_len;
+            const double v_mc = C->max_corr, v_cq = C->corr_q, v_cl = C->corr_l, v_f = C->freq, v_sd = C->std_dev;
+            const float v_ph = C->phase, v_amp = C->amplitude;
+            O->sweep = v_sweep;
+            O->delay = v_delay;
+            O->locked = v_locked;
+            O->ms_time = v_ms;
+            O->n_prev = v_prev;
+            O->max_corr = v_mc;
+            O->corr_q = v_cq;
+            O->corr_l = v_cl;
+            O->freq = v_f;
+            O->freq_weak = v_weak;
+            O->edge0 = v_e0;
+            O->edge_len = v_el;
+            O->phase = (double)v_ph;
+            O->amplitude = v_amp;
+            O->std_dev = (float)v_sd;
             O->reserved[0] = 0; O->reserved[1] = 0;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the record was written through the generic proxy
+        // the record was written through the generic proxy by warp 0 only (thread 0 and the PLL lanes): its fence
+        // orders those writes before the bulk copy; the other warps do not pay for a fence
+        if (t < 32) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (a.out_tma) {
             if (t == 0) {
