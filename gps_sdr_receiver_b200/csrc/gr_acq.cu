@@ -53,16 +53,16 @@ struct AcqArgs {
 // reference sample conversion, gpsrecv.py:168-173: complex64 / 127.5 - (1+1j).
 // numpy divides complex64 by the real scalar as  re * fl32(1/127.5)  (Smith's algorithm
 // with zero imaginary divisor), then subtracts 1 -- two separately rounded float32 ops.
-__device__ __forceinline__ float u8_to_f32(unsigned int b) {
-    const float scl = 1.0f / 127.5f;
-    return __fsub_rn(__fmul_rn((float)b, scl), 1.0f);
-}
-
 template <int IN_FMT>
 __device__ __forceinline__ cf load_sample(const void* base, long long n) {
     if (IN_FMT == GR_IN_U8IQ) {
-        const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(base) + n);
-        return cf{u8_to_f32(v.x), u8_to_f32(v.y)};
+        // byte -> integer-valued float by splicing it into the mantissa of 2^23 (PRMT + FADD, exact for 0..255): keeps
+        // the quarter-rate I2F unit out of the sample loop; then the reference's two float32 roundings
+        const unsigned v = __ldg(reinterpret_cast<const unsigned short*>(base) + n);
+        const float bi = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540)) - 8388608.0f;
+        const float bq = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7541)) - 8388608.0f;
+        const float scl = 1.0f / 127.5f;
+        return cf{__fsub_rn(__fmul_rn(bi, scl), 1.0f), __fsub_rn(__fmul_rn(bq, scl), 1.0f)};
     } else {
         const float2 v = __ldg(reinterpret_cast<const float2*>(base) + n);
         return cf{v.x, v.y};
@@ -164,28 +164,46 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
 #pragma unroll
         for (int j = 0; j < 16; ++j) s0[kOneBlock ? j : 0] = load_sample<IN_FMT>(src, base0 + 128 * j);
     }
+    cf* Rtab = smem + GR_B1_ELEMS + GR_B2_ELEMS;                    // [tcoh] block rotations of the current bin (multi-block form)
     for (int bin = bin0; bin < bin1; ++bin) {
         const float w32 = a.w32[bin];
         cf X[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) X[j] = cf{0.f, 0.f};
-        for (int i = 0; i < (kOneBlock ? 1 : a.tcoh); ++i) {
-            const long long base = base0 + (long long)i * GR_N;
-            cf s[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) s[j] = kOneBlock ? s0[kOneBlock ? j : 0] : load_sample<IN_FMT>(src, base + 128 * j);
+        if (kOneBlock) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const cf e = nco_fast(nco_arg(w32, base + 128 * j));      // exp(-i arg)
-                X[j].x += s[j].x * e.x - s[j].y * e.y;
-                X[j].y += s[j].y * e.x + s[j].x * e.y;
+                const cf e = nco_fast(nco_arg(w32, base0 + 128 * j));          // exp(-i arg)
+                X[j].x = s0[j].x * e.x - s0[j].y * e.y;
+                X[j].y = s0[j].y * e.x + s0[j].x * e.y;
             }
+        } else {
+            // tcoh > 1: sample n = n0 + 2048 i of block i is rotated by e(n0) * R_i, R_i = exp(-i w 2048 i / fs): 16 + tcoh
+            // sin/cos per thread and bin instead of 16 tcoh, and the fold is ONE complex FMA per sample.  (The float32
+            // rounding of the reference's per-sample phase argument, up to 3e-5 rad, is then not reproduced sample by
+            // sample; the effect on the correlation is below 1e-6 relative.)
+            for (int i = t; i < a.tcoh; i += GR_FFT_THREADS)
+                Rtab[i] = nco_fast(__fmul_rn(w32, __fdiv_rn((float)(i * GR_N), GR_FS)));
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) X[j] = cf{0.f, 0.f};
+            for (int i = 0; i < a.tcoh; ++i) {                     // 16 independent accumulators per block
+                const cf R = Rtab[i];
+                cf x[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x[j] = load_sample<IN_FMT>(src, base0 + (long long)i * GR_N + 128 * j);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    X[j].x = fmaf(x[j].x, R.x, X[j].x); X[j].x = fmaf(-x[j].y, R.y, X[j].x);
+                    X[j].y = fmaf(x[j].y, R.x, X[j].y); X[j].y = fmaf(x[j].x, R.y, X[j].y);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) X[j] = cmul(X[j], nco_fast(nco_arg(w32, base0 + 128 * j)));
         }
         fft2048<true>(X, smem, tw1, tw2, t);
         float4* d4 = reinterpret_cast<float4*>(a.spec + ((size_t)(rec * a.nbins + bin) * a.nnoncoh + k) * GR_N);
 #pragma unroll
         for (int m = 0; m < 8; ++m) d4[m * 128 + t] = make_float4(X[2 * m].x, X[2 * m].y, X[2 * m + 1].x, X[2 * m + 1].y);
-        __syncthreads();                                           // the FFT buffers are reused by the next bin
+        __syncthreads();                                           // the FFT buffers (and Rtab) are reused by the next bin
     }
 }
 
@@ -572,7 +590,9 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
     void (*fwd)(const AcqArgs) = p->in_format == GR_IN_U8IQ ? (one ? acq_fwd_kernel<GR_IN_U8IQ, true> : acq_fwd_kernel<GR_IN_U8IQ, false>)
                                                             : (one ? acq_fwd_kernel<GR_IN_CF32, true> : acq_fwd_kernel<GR_IN_CF32, false>);
     void (*inv)(const AcqArgs) = acq_inv_kernel<GR_ACQ_G, 6, 4>;
-    GR_CUDA(cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_FFT_SMEM_BYTES));
+    const size_t fwd_smem = GR_FFT_SMEM_BYTES + (one ? 0 : (size_t)p->tcoh * sizeof(cf));
+    if (fwd_smem > 200 * 1024) { gr_set_error("gr_acq_run_dev: tcoh too large"); return GR_ERR_ARG; }
+    GR_CUDA(cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
     GR_CUDA(cudaFuncSetAttribute(inv, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_ACQ_INV_SMEM));
     const size_t bps = p->in_format == GR_IN_U8IQ ? 2 : 8;
     p->last_launches = 0;
@@ -604,7 +624,7 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         const long long nfwd = units * a.nchunks;
         const long long ninv = (long long)nr * p->nbins * a.ngroups;
         if (nfwd > 0x7fffffffLL || ninv > 0x7fffffffLL) { gr_set_error("gr_acq_run_dev: grid too large"); return GR_ERR_ARG; }
-        fwd<<<(unsigned)nfwd, GR_FFT_THREADS, GR_FFT_SMEM_BYTES, s>>>(a);
+        fwd<<<(unsigned)nfwd, GR_FFT_THREADS, fwd_smem, s>>>(a);
         const long long ninv_grid = ninv < 4LL * gr_lib()->num_sms ? ninv : 4LL * gr_lib()->num_sms;
         inv<<<(unsigned)ninv_grid, GR_FFT_THREADS, GR_ACQ_INV_SMEM, s>>>(a);
         GR_CUDA(cudaGetLastError());
