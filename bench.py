@@ -233,7 +233,7 @@ def run_b200(args):
 
     # ---------------- acquisition (configs[1]) ----------------
     R, NBUF = args.recs, 8
-    sats = bench_sats(11 + rank)
+    sats = bench_sats(11)          # the same satellites on every rank (the validity checks below were exercised on them); noise differs per rank
     bufs = [synth.make_iq_dev(sats, R * NNONCOH * TCOH, noise_sigma=0.25, seed=1000 * rank + i, device=local) for i in range(NBUF)]
     plan = AcqPlan(PRNS, BINS, TCOH, NNONCOH, GR_ACQ_POW, device=local)
     best_dev = torch.empty((R, NPRN, ACQ_BEST.itemsize), dtype=torch.uint8, device=dev)
@@ -367,7 +367,7 @@ def run_b200(args):
     if not args.skip_tracking:
         n_ep = int(args.track_seconds * 1000) // TRACK_NCYC
         ngps = TRACK_NCYC * 2048
-        tsats = track_sats(7 + rank)
+        tsats = track_sats(7)       # same constellation on every rank, different noise
         rec = torch.empty(2 * n_ep * ngps, dtype=torch.uint8, device=dev)
         piece = 4000 * ngps
         for s0 in range(0, n_ep * ngps, piece):
