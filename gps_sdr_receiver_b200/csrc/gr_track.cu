@@ -27,6 +27,10 @@
 //   * The loop filter (arctan discriminator, pi-unwrap, lock detector, DF FIFO), the correlation
 //     quality FIFO, the sweep state machine and the edge detector run in the same kernel; only a
 //     gr_epoch_out record per channel and epoch leaves the SM.
+//   * Data movement: the epoch's raw block arrives in shared memory by TMA (cp.async.bulk + mbarrier) while the
+//     previous epoch's serial tail runs; the whole channel state (scalars + DF / CORRLST rings) is resident in
+//     shared memory for the life of the launch; the 448-byte record is assembled in shared memory and leaves by a
+//     TMA bulk store (no global store sits in front of a block barrier).
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
