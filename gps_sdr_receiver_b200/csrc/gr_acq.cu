@@ -160,9 +160,13 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
                           : (const void*)(reinterpret_cast<const float2*>(a.samples) + rec_off);
     const long long base0 = (long long)k * a.tcoh * GR_N + t;
     cf s0[kOneBlock ? 16 : 1];
+    float ts0[kOneBlock ? 16 : 1];                                 // fl32((n+1)/fs) of this thread's samples: bin-independent
     if (kOneBlock) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) s0[kOneBlock ? j : 0] = load_sample<IN_FMT>(src, base0 + 128 * j);
+        for (int j = 0; j < 16; ++j) {
+            s0[kOneBlock ? j : 0] = load_sample<IN_FMT>(src, base0 + 128 * j);
+            ts0[kOneBlock ? j : 0] = __fdiv_rn((float)(base0 + 128 * j + 1), GR_FS);
+        }
     }
     cf* Rtab = smem + GR_B1_ELEMS + GR_B2_ELEMS;                    // [tcoh] block rotations of the current bin (multi-block form)
     for (int bin = bin0; bin < bin1; ++bin) {
@@ -171,9 +175,9 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
         if (kOneBlock) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const cf e = nco_fast(nco_arg(w32, base0 + 128 * j));          // exp(-i arg)
-                X[j].x = s0[j].x * e.x - s0[j].y * e.y;
-                X[j].y = s0[j].y * e.x + s0[j].x * e.y;
+                const cf e = nco_fast(__fmul_rn(w32, ts0[kOneBlock ? j : 0]));   // exp(-i arg), arg as in nco_arg
+                X[j].x = s0[kOneBlock ? j : 0].x * e.x - s0[kOneBlock ? j : 0].y * e.y;
+                X[j].y = s0[kOneBlock ? j : 0].y * e.x + s0[kOneBlock ? j : 0].x * e.y;
             }
         } else {
             // tcoh > 1: sample n = n0 + 2048 i of block i is rotated by e(n0) * R_i, R_i = exp(-i w 2048 i / fs): 16 + tcoh
