@@ -317,7 +317,10 @@ def run_b200(args):
                 "d2h_bytes_per_step": R * NPRN * ACQ_BEST.itemsize, "api": "AcqPlan.search -> gr_acq_search_host (C ABI), pinned host buffers"},
         "gpu_launches": launches,
         "roofline": {"bound": "fp32", "kernel": "acq_inv_kernel (+ acq_fwd_kernel, 4 % of the launch pair)", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tf / fp32_peak, "traffic": None,
+                     "frac": achieved_tf / fp32_peak,
+                     # dram__bytes_read + dram__bytes_write of the kernel pair, ncu --set full capture of 128 recordings
+                     # (profiles/acq_r01_v3_ncu_summary.md: 5.3 + 801.8 MB forward, 864.9 + 11.1 MB inverse), scaled to R
+                     "traffic": R * (5.323008 + 801.842944 + 864.939008 + 11.087872) * 1e6 / 128,
                      "peak_source": f"measured in this run: register-resident FFMA chains on all SMs (gr_debug_fp32_peak); "
                                     f"theoretical at 1965 MHz = {FP32_PEAK_THEORY:.1f}",
                      "flop_per_cell": FLOP_PER_CELL, "ms_per_launch": ms_kernel,
@@ -440,7 +443,10 @@ def run_b200(args):
             "e2e": {"value": world * args.track_seconds / t_te2e, "unit": "x-realtime", "h2d_bytes": raw_bytes, "d2h_bytes": rec_bytes,
                     "gpu_launches": tl, "api": "TrackBank.process -> gr_track_process_host (3-stream chunk pipeline), pinned host buffers"},
             "roofline": {"bound": "hbm", "kernel": "track_kernel", "achieved": (raw_bytes + rec_bytes) / t_track / 1e9, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": (raw_bytes + rec_bytes) / t_track / 1e9 / hbm_peak, "traffic": None,
+                         "unit": "GB/s", "frac": (raw_bytes + rec_bytes) / t_track / 1e9 / hbm_peak,
+                         # ncu capture of 2000 epochs x 12 channels (profiles/track_r01_v5_ncu_summary.md): 66.3 MB read + 3.1 MB
+                         # written = the raw stream once (the 12 channels share it through L2) + the records not still in L2
+                         "traffic": n_ep * (66.262016 + 3.059456) * 1e6 / 2000,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "fallback",
                          "fp32_achieved_tflops": n_ep * TRACK_NCH * flop_ce / t_track / 1e12, "fp32_peak_tflops": fp32_peak,
                          "note": "BASELINE prescribes the HBM roofline; one recording is 12 CTAs running 75 000 dependent epochs, "
