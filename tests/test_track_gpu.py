@@ -208,3 +208,41 @@ def test_bank_argument_errors(gpu):
         bank.process(np.zeros(100, dtype=np.uint8), 8 * 2048, 1)
     empty = TrackBank(8, 2)
     assert empty.process(np.zeros(2 * 8 * 2048, dtype=np.uint8), 8 * 2048, 1).shape == (1, 0)
+
+
+def test_ncyc16_with_stream_gap_and_sweep_request_matches_oracle(gpu):
+    """N_CYC = 16 (the third stream length the reference allows, gpsglob.py:122-125) has no golden fixture: the bank is
+    compared with the oracle channel (pinned bit-exactly for N_CYC 32 and 8) epoch by epoch, across a dropped stream
+    (erasePrevData, gpslib.py:1143-1146) and a host-requested re-sweep (process(..., sweep=True))."""
+    from gps_sdr_receiver_b200 import synth
+    from gps_sdr_receiver_b200.tracking import TrackBank
+    n_cyc, ngps = 16, 16 * 2048
+    sats = [synth.Sat(prn=6, doppler=2310.0, delay=333.3, amp=0.08, bit_offset_ms=9, bit_seed=1),
+            synth.Sat(prn=27, doppler=-1490.0, delay=1801.6, amp=0.08, bit_offset_ms=2, bit_seed=2)]
+    n_ep = 150
+    raw = synth.make_iq(sats, n_ep * n_cyc, seed=21)
+    init = [(6, 2300.0, 334), (27, -1500.0, 1802)]
+    bank = TrackBank(n_cyc, 4)
+    slots = [bank.add(p, f, d) for p, f, d in init]
+    chans = [orc.Channel(p, f, delay=d, n_cyc=n_cyc) for p, f, d in init]
+    # three calls: epochs 0..59, then a gap of one stream (epoch 60 dropped), epochs 61..99, sweep request on channel 1, 100..149
+    plan = [(0, 60, False), (61, 100, False), (100, 150, True)]
+    for e0, e1, sweep in plan:
+        if sweep:
+            bank.request_sweep(slots[1])
+        recs = bank.process(raw[2 * e0 * ngps:2 * e1 * ngps], (e0 + 1) * ngps, n_epochs=e1 - e0)
+        for e in range(e0, e1):
+            blk = orc.raw_to_complex(raw[2 * e * ngps:2 * (e + 1) * ngps])
+            for c, ch in enumerate(chans):
+                sw, _, cp, (cq, cl) = ch.process(blk, np.int64((e + 1) * ngps), sweep=(sweep and c == 1 and e == e0))
+                r = recs[e - e0, c]
+                tag = (e, c)
+                assert bool(r["sweep"]) == bool(sw) and int(r["delay"]) == ch.delay and bool(r["locked"]) == bool(ch.locked), tag
+                assert int(r["ms_time"]) == ch.ms_time and int(r["n_prev"]) == len(ch.prev_samples), tag
+                assert (r["code_phase"] >= 0) == (cp >= 0) and r["corr_q"] == cq and r["corr_l"] == cl, tag
+                if cp >= 0:
+                    assert abs(r["code_phase"] - cp) < 2e-4, tag
+                assert abs(r["freq"] - float(ch.freq)) <= 1e-6 * abs(float(ch.freq)) + 1e-3, tag
+                assert abs(r["max_corr"] - ch.max_corr) <= 1e-4 * abs(ch.max_corr) + 1e-6, tag
+    assert all(ch.locked for ch in chans)
+    bank.close()
