@@ -296,6 +296,13 @@ __device__ __forceinline__ void twiddle8(cf* v, int k0, const cf* tw, uint32_t t
     }
 }
 
+// v[k0..k0+7] *= the eight twiddles in w (interleaved re, im); k = 0 is the trivial one
+__device__ __forceinline__ void twiddle8_regs(cf* v, int k0, const float* w) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k0 + k != 0) v[k0 + k] = cmul(v[k0 + k], cf{w[2 * k], w[2 * k + 1]});
+}
+
 // Forward spectra staged by TMA: one thread issues a 16 KiB cp.async.bulk for X_{k+1} into a shared-memory
 // stage right after the exchange-1 barrier of transform k (every thread has consumed X_k by then); completion
 // is tracked by an mbarrier, and the conjugate code spectrum is fetched from TMEM before the wait.  No
@@ -439,13 +446,24 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
                 y[8 + j].x = x1.x * c1.y + x1.y * c1.x;
                 y[8 + j].y = x1.x * c1.x - x1.y * c1.y;
             }
-            // ---- FFT-2048 (gr_fft2048t.cuh) ----
+            // ---- FFT-2048 (gr_fft2048t.cuh); TMEM-resident twiddles are fetched one step ahead of their use ----
+            float wa[16], wb[16];
+            if (TM & 4) tm_ld16_issue(tm + kColTw1, wa);
             dft16(y);
-            twiddle8<(TM & 4) != 0>(y, 0, tw1, tm + kColTw1);
-            twiddle8<(TM & 4) != 0>(y, 8, tw1, tm + kColTw1);
+            if (TM & 4) {
+                tm_ld_wait16(wa);
+                tm_ld16_issue(tm + kColTw1 + 16, wb);
+                twiddle8_regs(y, 0, wa);
+                tm_ld_wait16(wb);
+                twiddle8_regs(y, 8, wb);
+            } else {
+                twiddle8<false>(y, 0, tw1, 0);
+                twiddle8<false>(y, 8, tw1, 0);
+            }
             float4* b1 = buf1 + par * (GR_W_BUF1_BYTES / 16);
             par ^= 1;
             fftw_ex1_write(b1, t, y);
+            if (TM & 2) tm_ld16_issue(tm + kColTw2, wa);         // arrives while the block waits at the barrier
             __syncthreads();
             if (t == 0) {                                        // every thread has consumed X_k: refill the stage
                 if (k + 1 < a.nnoncoh) {
@@ -459,8 +477,16 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             }
             fftt_ex1_read(b1, t, y);
             dft16(y);
-            twiddle8<(TM & 2) != 0>(y, 0, tw2, tm + kColTw2);
-            twiddle8<(TM & 2) != 0>(y, 8, tw2, tm + kColTw2);
+            if (TM & 2) {
+                tm_ld_wait16(wa);
+                tm_ld16_issue(tm + kColTw2 + 16, wb);
+                twiddle8_regs(y, 0, wa);
+                tm_ld_wait16(wb);
+                twiddle8_regs(y, 8, wb);
+            } else {
+                twiddle8<false>(y, 0, tw2, 0);
+                twiddle8<false>(y, 8, tw2, 0);
+            }
             fftt_ex2_stage3(tm + kColX, y);
             float p[16];
             if (a.mode == GR_ACQ_POW) {
