@@ -319,8 +319,8 @@ def run_b200(args):
         "roofline": {"bound": "fp32", "kernel": "acq_inv_kernel (+ acq_fwd_kernel, 4 % of the launch pair)", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp32_peak,
                      # dram__bytes_read + dram__bytes_write of the kernel pair, ncu --set full capture of 128 recordings
-                     # (profiles/acq_r01_v3_ncu_summary.md: 5.3 + 801.8 MB forward, 864.9 + 11.1 MB inverse), scaled to R
-                     "traffic": R * (5.323008 + 801.842944 + 864.939008 + 11.087872) * 1e6 / 128,
+                     # (profiles/acq_r01_v4_ncu_summary.md: 5.3 + 801.8 MB forward, 865.2 + 9.4 MB inverse), scaled to R
+                     "traffic": R * (5.3 + 801.8 + 865.2 + 9.4) * 1e6 / 128,
                      "peak_source": f"measured in this run: register-resident FFMA chains on all SMs (gr_debug_fp32_peak); "
                                     f"theoretical at 1965 MHz = {FP32_PEAK_THEORY:.1f}",
                      "flop_per_cell": FLOP_PER_CELL, "ms_per_launch": ms_kernel,

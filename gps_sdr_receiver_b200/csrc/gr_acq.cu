@@ -342,20 +342,12 @@ __device__ __forceinline__ void tm_ld_wait16(float* r) {      // the registers b
 // FFT: gr_fft2048t.cuh (exchange 1 in shared memory with 128-bit stores on a double-buffered 16 KiB buffer and
 // ONE block barrier per transform; exchange 2 + radix-8 through TMEM).  TM bit 1 / bit 2: stage-2 / stage-1
 // twiddles in TMEM (else registers).
-#define GR_ACQ_INV_SMEM (3 * GR_W_BUF1_BYTES + GR_N * 2)   // 2 x exchange-1 buffer + forward-spectrum stage + 8 of 16 accumulators = 52 KiB
-// Persistent: the grid is 4 CTAs per SM; a CTA walks over work items (recording, Doppler bin, PRN group) with a
-// grid stride, keeping its TMEM allocation and twiddles.  One "job" = one PRN of a work item = nnoncoh
-// transforms.  The next job's conjugate spectrum is loaded from L2 while the current job's cell statistics
-// are being reduced, and the next job's first forward spectrum is already in flight (TMA) by then.
+#define GR_ACQ_INV_SMEM (3 * GR_W_BUF1_BYTES)      // 2 x exchange-1 buffer + forward-spectrum stage = 48 KiB
 template <int G, int TM, int MINB>
 __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const AcqArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* buf1 = reinterpret_cast<float4*>(smem_raw);                         // 2 x 16 KiB
     float4* xs = reinterpret_cast<float4*>(smem_raw + 2 * GR_W_BUF1_BYTES);      // forward-spectrum stage, 16 KiB
-    // non-coherent accumulators: 8 of the 16 per thread live in shared memory ([2][128] float4, thread-private
-    // slots) -- at the 128-register cap of 4 CTAs / SM ptxas was spilling accumulators to local memory, and
-    // all 16 in shared memory would not leave room for 4 CTAs (4 x 57 KiB > 228 KiB)
-    float4* accs = reinterpret_cast<float4*>(smem_raw + 3 * GR_W_BUF1_BYTES) + threadIdx.x;
     __shared__ __align__(8) uint64_t xbar;
     __shared__ AcqScratch scratch;
     __shared__ uint32_t tm_base_sh;
@@ -417,11 +409,9 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
     int g = 0;
 
     while (true) {
+        float acc[16];                                          // non-coherent accumulators, 16 lags per thread
 #pragma unroll
-        for (int q = 0; q < 2; ++q) accs[128 * q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        float accr[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) accr[j] = 0.f;
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
         for (int k = 0; k < a.nnoncoh; ++k) {
             cf y[16];
             float w0[16], w1[16];
@@ -488,22 +478,13 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
                 twiddle8<false>(y, 8, tw2, 0);
             }
             fftt_ex2_stage3(tm + kColX, y);
-            float p[16];
             if (a.mode == GR_ACQ_POW) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) p[j] = y[j].x * y[j].x + y[j].y * y[j].y;
+                for (int j = 0; j < 16; ++j) acc[j] += y[j].x * y[j].x + y[j].y * y[j].y;
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) p[j] = sqrtf(y[j].x * y[j].x + y[j].y * y[j].y);
+                for (int j = 0; j < 16; ++j) acc[j] += sqrtf(y[j].x * y[j].x + y[j].y * y[j].y);
             }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                float4 v = accs[128 * q];
-                v.x += p[4 * q]; v.y += p[4 * q + 1]; v.z += p[4 * q + 2]; v.w += p[4 * q + 3];
-                accs[128 * q] = v;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) accr[j] += p[8 + j];
         }
         // the job after this one; its conjugate spectrum is loaded now: L2 latency hidden behind the cell reduction
         int n_work = work, n_g = g + 1;
@@ -519,14 +500,8 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
                 w[2 * j] = v.x; w[2 * j + 1] = v.y;
             }
         }
-        float acc[16];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const float4 v = accs[128 * q];
-            acc[4 * q] = v.x * sc; acc[4 * q + 1] = v.y * sc; acc[4 * q + 2] = v.z * sc; acc[4 * q + 3] = v.w * sc;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[8 + j] = accr[j] * sc;
+        for (int j = 0; j < 16; ++j) acc[j] *= sc;
         acq_cell_epilogue(acc, obase, t, a.out + ((size_t)rec * a.nprn + grp * G + g) * a.nbins + bin, &scratch);
         if (!has_next) break;
         tm_st16(tm + kColC, w);
