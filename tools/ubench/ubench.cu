@@ -309,6 +309,80 @@ __global__ void __launch_bounds__(128, 4) k_inv(float* out, const float2* tw1p, 
     if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base_sh), "r"(128));
 }
 
+// ---- 9. warp placement of the inverse loop: where do the 4 warps of one transform sit? ----
+// MAP 0: 128-thread CTAs, 4 per SM (product kernel): the 4 warps of a transform sit on the 4 schedulers, each scheduler
+//        interleaves 4 independent transforms.
+// MAP 1: one 512-thread CTA, transform group = 4 CONSECUTIVE warps (same placement as MAP 0, named barriers).
+// MAP 2: one 512-thread CTA, transform group = warps {g, g+4, g+8, g+12}: all 4 warps of a transform on ONE scheduler.
+template <int MAP>
+__global__ void __launch_bounds__(MAP == 0 ? 128 : 512, MAP == 0 ? 4 : 1) k_place(float* out, const float2* tw1p, const float2* tw2p, int iters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t tm_base_sh;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    int grp, wig;                                        // transform group inside the CTA, warp inside the group
+    if (MAP == 0) { grp = 0; wig = warp; }
+    else if (MAP == 1) { grp = warp >> 2; wig = warp & 3; }
+    else { grp = warp & 3; wig = warp >> 2; }
+    const int t = 32 * wig + lane;                       // thread index inside the transform
+    float4* buf1 = reinterpret_cast<float4*>(smem_raw + (size_t)grp * 2 * GR_W_BUF1_BYTES);
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tm_base_sh)),
+                     "r"(MAP == 0 ? 128 : 512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // TMEM: lane quadrant = hardware warp % 4; warps sharing a quadrant (MAP 1, 2: 4 of them) take 128 columns each
+    const uint32_t tm = tm_base_sh + ((uint32_t)(32 * (warp & 3)) << 16) + (MAP == 0 ? 0 : 128 * (warp >> 2));
+    {
+        float w[32];
+        for (int i = 0; i < 16; ++i) { const float2 u = tw1p[t * 16 + i]; w[2 * i] = u.x; w[2 * i + 1] = u.y; }
+        u_tm_st16(tm + 96, w); u_tm_st16(tm + 112, w + 16);
+        for (int i = 0; i < 16; ++i) { const float2 u = tw2p[(t & 7) * 16 + i]; w[2 * i] = u.x; w[2 * i + 1] = u.y; }
+        u_tm_st16(tm + 64, w); u_tm_st16(tm + 80, w + 16);
+        u_tm_st16(tm, w); u_tm_st16(tm + 16, w + 16);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    float acc[16];
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    int par = 0;
+    for (int it = 0; it < iters; ++it) {
+        cf y[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y[j] = cf{acc[j] * 1e-3f + (float)j, acc[(j + 1) & 15] * 1e-3f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float w[16];
+            u_tm_ld16(tm + 16 * h, w);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const cf cc = cf{w[2 * j], w[2 * j + 1]}; const cf x = y[8 * h + j];
+                y[8 * h + j].x = x.x * cc.y + x.y * cc.x; y[8 * h + j].y = x.x * cc.x - x.y * cc.y;
+            }
+        }
+        dft16(y);
+        u_tw8(y, 0, tm + 96); u_tw8(y, 8, tm + 96);
+        float4* b1 = buf1 + par * (GR_W_BUF1_BYTES / 16);
+        par ^= 1;
+        fftw_ex1_write(b1, t, y);
+        if (MAP == 0) __syncthreads(); else asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+        fftt_ex1_read(b1, t, y);
+        dft16(y);
+        u_tw8(y, 0, tm + 64); u_tw8(y, 8, tm + 64);
+        fftt_ex2_stage3(tm + 32, y);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += y[j].x * y[j].x + y[j].y * y[j].y;
+    }
+    float s = 0.f;
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 1.2345f) out[0] = s;
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base_sh), "r"(MAP == 0 ? 128 : 512));
+}
+
 template <typename F>
 static float time_ms(F launch) {
     cudaEvent_t e0, e1;
@@ -377,6 +451,17 @@ int main() {
         RUN_ABL(1 | 8 | 16, "-X -ex1 -ex2");
         RUN_ABL(1 | 2 | 4 | 8 | 16, "math only (dft+acc)");
         RUN_ABL(64 | 2 | 4 | 32, "data movement only");
+    }
+
+    {   // warp placement (no X stage: y is synthesised in registers, everything else as in the product loop)
+        const int it2 = 2000;
+        auto rep3 = [&](const char* name, float ms) { printf("placement %-44s %.3f ms  cycles/transform/SM=%.1f\n", name, ms, ms * 1e-3 * ghz * 1e9 / it2 / 4); };
+        CK(cudaFuncSetAttribute(k_place<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * GR_W_BUF1_BYTES));
+        CK(cudaFuncSetAttribute(k_place<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GR_W_BUF1_BYTES));
+        CK(cudaFuncSetAttribute(k_place<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GR_W_BUF1_BYTES));
+        rep3("4 CTAs x 128: transform across 4 schedulers", time_ms([&] { k_place<0><<<sms * 4, 128, 2 * GR_W_BUF1_BYTES>>>(d_out, d_tw, d_tw, it2); }));
+        rep3("1 CTA x 512: consecutive warps (same placement)", time_ms([&] { k_place<1><<<sms, 512, 8 * GR_W_BUF1_BYTES>>>(d_out, d_tw, d_tw, it2); }));
+        rep3("1 CTA x 512: one transform per scheduler", time_ms([&] { k_place<2><<<sms, 512, 8 * GR_W_BUF1_BYTES>>>(d_out, d_tw, d_tw, it2); }));
     }
     return 0;
 }
