@@ -383,6 +383,133 @@ __global__ void __launch_bounds__(MAP == 0 ? 128 : 512, MAP == 0 ? 4 : 1) k_plac
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base_sh), "r"(MAP == 0 ? 128 : 512));
 }
 
+// ---- 10. two transforms per thread (2 PRNs sharing twiddle fetches, barrier and TMEM waits), 2 CTAs / SM, up to 255 regs ----
+__device__ __forceinline__ void u_tm_ld16_issue(uint32_t taddr, float* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+          "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void u_tm_wait16(float* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+                   "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]));
+}
+__device__ __forceinline__ void u_mul8(cf* v, int k0, const float* w) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k0 + k != 0) v[k0 + k] = cmul(v[k0 + k], cf{w[2 * k], w[2 * k + 1]});
+}
+__device__ __forceinline__ void u_pack(const cf* v, float* r) {
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+        const int K = 8 * ((k2 >> 2) & 1) + 4 * ((k2 >> 1) & 1) + 2 * ((k2 >> 3) & 1) + (k2 & 1);
+        r[2 * K] = v[k2].x; r[2 * K + 1] = v[k2].y;
+    }
+}
+__device__ __forceinline__ void u_unpack_dft8(const float* r, cf* v) {
+    cf a[8], b[8];
+#pragma unroll
+    for (int n3 = 0; n3 < 8; ++n3) {
+        const int K = 4 * (n3 & 1) + 2 * (n3 >> 2) + ((n3 >> 1) & 1);
+        a[n3] = cf{r[2 * K], r[2 * K + 1]};
+        b[n3] = cf{r[2 * (8 + K)], r[2 * (8 + K) + 1]};
+    }
+    dft8(a); dft8(b);
+#pragma unroll
+    for (int k3 = 0; k3 < 8; ++k3) { v[2 * k3] = a[k3]; v[2 * k3 + 1] = b[k3]; }
+}
+__device__ __forceinline__ void u_ld32_issue(uint32_t taddr, float* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]),
+          "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]), "=f"(r[17]), "=f"(r[18]),
+          "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]),
+          "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+        : "r"(taddr), "r"(taddr + 16));
+}
+__device__ __forceinline__ void u_wait32(float* r) { u_tm_wait16(r); u_tm_wait16(r + 16); }
+
+__global__ void __launch_bounds__(128, 2) k_2t(float* out, const float2* tw1p, const float2* tw2p, int iters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* buf1 = reinterpret_cast<float4*>(smem_raw);          // [2 transforms][2 parities] x 16 KiB
+    __shared__ uint32_t tm_base_sh;
+    const int t = threadIdx.x;
+    if (t < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tm_base_sh)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tm = tm_base_sh + ((uint32_t)(32 * (t >> 5)) << 16);
+    // columns: c0 0..31 | c1 32..63 | exch0 64..95 | exch1 96..127 | tw2 128..159 | tw1 160..191
+    {
+        float w[32];
+        for (int i = 0; i < 16; ++i) { const float2 u = tw1p[t * 16 + i]; w[2 * i] = u.x; w[2 * i + 1] = u.y; }
+        u_tm_st16(tm + 160, w); u_tm_st16(tm + 176, w + 16);
+        for (int i = 0; i < 16; ++i) { const float2 u = tw2p[(t & 7) * 16 + i]; w[2 * i] = u.x; w[2 * i + 1] = u.y; }
+        u_tm_st16(tm + 128, w); u_tm_st16(tm + 144, w + 16);
+        u_tm_st16(tm, w); u_tm_st16(tm + 16, w + 16); u_tm_st16(tm + 32, w); u_tm_st16(tm + 48, w + 16);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    float acc0[16], acc1[16];
+    for (int j = 0; j < 16; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+    int par = 0;
+    for (int it = 0; it < iters; ++it) {
+        cf x[16], y0[16], y1[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = cf{acc0[j] * 1e-3f + (float)j, acc1[(j + 1) & 15] * 1e-3f};
+        float wa[16], wb[16];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                      // y0 = x c0, y1 = x c1
+            u_tm_ld16_issue(tm + 16 * h, wa); u_tm_ld16_issue(tm + 32 + 16 * h, wb);
+            u_tm_wait16(wa); u_tm_wait16(wb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const cf xx = x[8 * h + j];
+                y0[8 * h + j] = cf{xx.x * wa[2 * j + 1] + xx.y * wa[2 * j], xx.x * wa[2 * j] - xx.y * wa[2 * j + 1]};
+                y1[8 * h + j] = cf{xx.x * wb[2 * j + 1] + xx.y * wb[2 * j], xx.x * wb[2 * j] - xx.y * wb[2 * j + 1]};
+            }
+        }
+        u_tm_ld16_issue(tm + 160, wa); u_tm_ld16_issue(tm + 176, wb);      // stage-1 twiddles, shared by both transforms
+        dft16(y0); dft16(y1);
+        u_tm_wait16(wa); u_tm_wait16(wb);
+        u_mul8(y0, 0, wa); u_mul8(y1, 0, wa); u_mul8(y0, 8, wb); u_mul8(y1, 8, wb);
+        float4* b0 = buf1 + par * (GR_W_BUF1_BYTES / 16);
+        float4* b1 = buf1 + (2 + par) * (GR_W_BUF1_BYTES / 16);
+        par ^= 1;
+        fftw_ex1_write(b0, t, y0); fftw_ex1_write(b1, t, y1);
+        u_tm_ld16_issue(tm + 128, wa); u_tm_ld16_issue(tm + 144, wb);      // stage-2 twiddles
+        __syncthreads();
+        fftt_ex1_read(b0, t, y0); fftt_ex1_read(b1, t, y1);
+        dft16(y0); dft16(y1);
+        u_tm_wait16(wa); u_tm_wait16(wb);
+        u_mul8(y0, 0, wa); u_mul8(y1, 0, wa); u_mul8(y0, 8, wb); u_mul8(y1, 8, wb);
+        float r0[32], r1[32];
+        u_pack(y0, r0); u_pack(y1, r1);
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {          // both transposes share every wait
+            tm_st_16x256b_x4(tm + 64, r0); tm_st_16x256b_x4(tm + 64 + (16u << 16), r0 + 16);
+            tm_st_16x256b_x4(tm + 96, r1); tm_st_16x256b_x4(tm + 96 + (16u << 16), r1 + 16);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            u_ld32_issue(tm + 64, r0); u_ld32_issue(tm + 96, r1);
+            u_wait32(r0); u_wait32(r1);
+        }
+        u_unpack_dft8(r0, y0); u_unpack_dft8(r1, y1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { acc0[j] += y0[j].x * y0[j].x + y0[j].y * y0[j].y; acc1[j] += y1[j].x * y1[j].x + y1[j].y * y1[j].y; }
+    }
+    float s = 0.f;
+    for (int i = 0; i < 16; ++i) s += acc0[i] + acc1[i];
+    if (s == 1.2345f) out[0] = s;
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base_sh), "r"(256));
+}
+
 template <typename F>
 static float time_ms(F launch) {
     cudaEvent_t e0, e1;
@@ -462,6 +589,13 @@ int main() {
         rep3("4 CTAs x 128: transform across 4 schedulers", time_ms([&] { k_place<0><<<sms * 4, 128, 2 * GR_W_BUF1_BYTES>>>(d_out, d_tw, d_tw, it2); }));
         rep3("1 CTA x 512: consecutive warps (same placement)", time_ms([&] { k_place<1><<<sms, 512, 8 * GR_W_BUF1_BYTES>>>(d_out, d_tw, d_tw, it2); }));
         rep3("1 CTA x 512: one transform per scheduler", time_ms([&] { k_place<2><<<sms, 512, 8 * GR_W_BUF1_BYTES>>>(d_out, d_tw, d_tw, it2); }));
+    }
+
+    {   // two transforms per thread, 2 CTAs / SM
+        const int it2 = 2000;
+        CK(cudaFuncSetAttribute(k_2t, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GR_W_BUF1_BYTES));
+        const float ms = time_ms([&] { k_2t<<<sms * 2, 128, 4 * GR_W_BUF1_BYTES>>>(d_out, d_tw, d_tw, it2); });
+        printf("two-per-thread 2 CTAs x 128 x 2 transforms             %.3f ms  cycles/transform/SM=%.1f\n", ms, ms * 1e-3 * ghz * 1e9 / it2 / 4);
     }
     return 0;
 }
