@@ -68,3 +68,34 @@ def test_encoder_round_trip_matches_the_quantised_ephemeris(gold):
     bad = bits[:300].copy()
     bad[200] ^= 1
     assert navbits.decode_subframe(bad)[0] == 3 and navbits.decode_subframe(bits[:299])[0] == 1
+
+
+def test_random_ephemerides_round_trip_and_single_bit_errors_are_caught():
+    """Property check: any quantised ephemeris survives encode -> decode; any single bit error in words 2..10 of a
+    subframe is caught by the parity (word 1 is not parity-checked by the reference decoder, gpslib.py:379-405)."""
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        eph = dict(weekNum=int(rng.integers(0, 1024)), satAcc=int(rng.integers(0, 16)), satHealth=int(rng.integers(0, 64)),
+                   Tgd=int(rng.integers(-128, 128)) * 2.0 ** -31, IODC=int(rng.integers(0, 1024)), Toc=int(rng.integers(0, 37800)) * 16,
+                   af2=int(rng.integers(-128, 128)) * 2.0 ** -55, af1=int(rng.integers(-2 ** 15, 2 ** 15)) * 2.0 ** -43,
+                   af0=int(rng.integers(-2 ** 21, 2 ** 21)) * 2.0 ** -31, IODE2=int(rng.integers(0, 256)),
+                   Crs=int(rng.integers(-2 ** 15, 2 ** 15)) * 2.0 ** -5, deltaN=int(rng.integers(-2 ** 15, 2 ** 15)) * 2.0 ** -43 * navbits.GPS_PI,
+                   M0=int(rng.integers(-2 ** 31, 2 ** 31)) * 2.0 ** -31 * navbits.GPS_PI, Cuc=int(rng.integers(-2 ** 15, 2 ** 15)) * 2.0 ** -29,
+                   e=int(rng.integers(0, 2 ** 32)) * 2 ** -33, Cus=int(rng.integers(-2 ** 15, 2 ** 15)) * 2.0 ** -29,
+                   sqrtA=int(rng.integers(0, 2 ** 32)) * 2.0 ** -19, Toe=int(rng.integers(0, 37800)) * 16,
+                   Cic=int(rng.integers(-2 ** 15, 2 ** 15)) * 2.0 ** -29, omegaBig=int(rng.integers(-2 ** 31, 2 ** 31)) * 2.0 ** -31 * navbits.GPS_PI,
+                   Cis=int(rng.integers(-2 ** 15, 2 ** 15)) * 2.0 ** -29, i0=int(rng.integers(-2 ** 31, 2 ** 31)) * 2.0 ** -31 * navbits.GPS_PI,
+                   IODE3=int(rng.integers(0, 256)), Crc=int(rng.integers(-2 ** 15, 2 ** 15)) * 2.0 ** -5,
+                   omegaSmall=int(rng.integers(-2 ** 31, 2 ** 31)) * 2.0 ** -31 * navbits.GPS_PI,
+                   omegaDot=int(rng.integers(-2 ** 23, 2 ** 23)) * 2.0 ** -43 * navbits.GPS_PI,
+                   IDOT=int(rng.integers(-2 ** 13, 2 ** 13)) * 2.0 ** -43 * navbits.GPS_PI)
+        tow = int(rng.integers(0, 100800))
+        for sf_id in (1, 2, 3, 4, 5):
+            bits = np.asarray(navbits.encode_subframe(sf_id, tow, eph), dtype=np.int8)
+            status, f = navbits.decode_subframe(bits)
+            assert status == 0 and f["ID"] == sf_id and f["tow"] == tow
+            assert all(f[k] == eph[k] for k in f if k in eph), (trial, sf_id, {k: (f[k], eph[k]) for k in f if k in eph and f[k] != eph[k]})
+            pos = int(rng.integers(30, 300))
+            bad = bits.copy()
+            bad[pos] ^= 1
+            assert navbits.decode_subframe(bad)[0] == 3, (trial, sf_id, pos)
