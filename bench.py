@@ -139,7 +139,7 @@ def cpu_acq_baseline(min_seconds: float = 10.0):
 
 def _cpu_track_worker(job):
     """One worker process = the channels the reference would give to one pool process (gpsrecv.py:300-334)."""
-    idx, seconds = job
+    idx, seconds, repeats = job
     from gps_sdr_receiver_b200 import synth
     from oracle import gps_oracle as orc
     sats = track_sats(7)
@@ -149,27 +149,28 @@ def _cpu_track_worker(job):
     chans = [orc.Channel(sats[i].prn, 50.0 * np.round(sats[i].doppler / 50.0), delay=(int(sats[i].delay) + 1) % 2048, n_cyc=TRACK_NCYC)
              for i in idx]
     t0 = time.perf_counter()
-    for e in range(n_ep):
-        data = orc.raw_to_complex(raw[e * 2 * ngps:(e + 1) * 2 * ngps])
-        for ch in chans:
-            ch.process(data, np.int64((e + 1) * ngps))
+    for rep in range(repeats):                                   # the same samples again: timing only, stream numbers go on
+        for e in range(n_ep):
+            data = orc.raw_to_complex(raw[e * 2 * ngps:(e + 1) * 2 * ngps])
+            for ch in chans:
+                ch.process(data, np.int64((rep * n_ep + e + 1) * ngps))
     return time.perf_counter() - t0
 
 
-def cpu_track_baseline(sats, seconds: float = 2.0):
+def cpu_track_baseline(sats, seconds: float = 2.0, repeats: int = 10):
     """12 channels spread over one worker process per host core (at most one per channel), the reference's pool
     architecture (gpsrecv.py:340-417) with the oracle's restatement of SatStream.process in the workers."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, len(sats)))
-    jobs = [([i for i in range(len(sats)) if i % workers == w], seconds) for w in range(workers)]
+    jobs = [([i for i in range(len(sats)) if i % workers == w], seconds, repeats) for w in range(workers)]
     with mp.get_context("spawn").Pool(workers) as pool:
-        pool.map(_cpu_track_worker, [([0], 0.1)] * workers)      # warm the workers (imports, code spectra)
+        pool.map(_cpu_track_worker, [([0], 0.1, 1)] * workers)   # warm the workers (imports, code spectra)
         dts = pool.map(_cpu_track_worker, jobs)
     dt = max(dts)
-    n_ep = int(seconds * 1000) // TRACK_NCYC
+    n_ep = repeats * (int(seconds * 1000) // TRACK_NCYC)
     return {"value": n_ep * TRACK_NCYC * 1e-3 / dt, "unit": "x-realtime", "cores": workers, "kind": "port",
-            "sample": f"{n_ep} epochs x {len(sats)} channels (N_CYC=8), one worker process per core ({workers}), each running "
+            "sample": f"{n_ep} epochs ({seconds:.0f} s of samples x {repeats}) x {len(sats)} channels (N_CYC=8), one worker process per core ({workers}), each running "
                       f"oracle.Channel.process (restatement of gpslib.SatStream.process) for its channels; slowest worker {dt:.1f} s"}
 
 
