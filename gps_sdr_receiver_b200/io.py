@@ -122,3 +122,38 @@ class FileReceiver:
             for st in streams:
                 st.close()
             bank.close()
+
+
+def main(argv=None) -> int:
+    """`python -m gps_sdr_receiver_b200.io recording.bin [--ip 127.0.0.1] [--port 61431] [--start-stream N] [--n-cyc 32]`:
+    the headless replacement of `gpsrecv.py` for a recorded file -- the reference's `gpseval.py` (and its GUI) can
+    listen on the UDP port unchanged."""
+    import argparse
+    ap = argparse.ArgumentParser(description=main.__doc__)
+    ap.add_argument("recording")
+    ap.add_argument("--ip", default="127.0.0.1")
+    ap.add_argument("--port", type=int, default=UDP_PORT)
+    ap.add_argument("--start-stream", type=int, default=0)
+    ap.add_argument("--n-cyc", type=int, default=32)
+    ap.add_argument("--max-sat", type=int, default=glob.MAX_SAT)
+    ap.add_argument("--quiet", action="store_true")
+    a = ap.parse_args(argv)
+    rx = FileReceiver(a.recording, n_cyc=a.n_cyc, max_sat=a.max_sat, start_stream=a.start_stream)
+    sock = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    n = 0
+    try:
+        for skipped, frame_lst, coph_lst in rx.messages():
+            send_udp(encode_message(skipped, frame_lst, coph_lst), a.ip, a.port, sock)
+            n += 1
+            if not a.quiet:
+                ids = [(f["SAT"], f["ID"], f["tow"]) for f in frame_lst if "ID" in f]
+                print(f"message {n}: {len(frame_lst)} frame dicts, subframes {ids}, code phases of {sorted(coph_lst)}")
+    finally:
+        sock.close()
+    if not a.quiet:
+        print(f"satellites tracked: {[(prn, f) for _, prn, f, _ in rx.found]}; {n} messages sent to {a.ip}:{a.port}")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
