@@ -67,3 +67,27 @@ def test_file_receiver_messages_match_per_stream_processing(gpu, tmp_path):
         assert got_frames == frames[:len(got_frames)] and len(got_frames) >= len(frames) - 1
         _check_frames([{k: v for k, v in f.items() if k not in ("SAT", "AMP", "CRM", "FRQ", "SWP")} for f in got_frames if "ID" in f],
                       sat, rolled=(prn == sats[1].prn))
+
+
+@pytest.mark.gpu
+def test_command_line_receiver_sends_the_messages_over_udp(gpu, tmp_path):
+    import socket
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_nav_e2e import N_CYC, _recording
+    sats, raw = _recording()
+    p = tmp_path / "rec.bin"
+    raw[:2 * N_CYC * 2048 * 160].tofile(p)                            # 5.1 s
+    listener = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    listener.bind(("127.0.0.1", 0))
+    listener.settimeout(5.0)
+    port = listener.getsockname()[1]
+    assert gio.main([str(p), "--port", str(port), "--n-cyc", str(N_CYC), "--max-sat", "4", "--quiet"]) == 0
+    got = []
+    for _ in range(160 // (1024 // N_CYC)):
+        skipped, frame_lst, coph_lst = pickle.loads(listener.recv(gio.UDP_BUFSIZE))
+        got.append((skipped, frame_lst, coph_lst))
+    listener.close()
+    assert len(got) == 5 and all(m[0] == 0 for m in got)
+    assert {f["SAT"] for m in got for f in m[1]} == {s.prn for s in sats}
+    assert all(len(v) > 0 for m in got for v in m[2].values())
