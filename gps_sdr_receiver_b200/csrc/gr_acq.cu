@@ -303,6 +303,12 @@ __device__ __forceinline__ void twiddle8_regs(cf* v, int k0, const float* w) {
         if (k0 + k != 0) v[k0 + k] = cmul(v[k0 + k], cf{w[2 * k], w[2 * k + 1]});
 }
 
+__device__ __forceinline__ void twiddle8_pk(cpk* v, int k0, const float* w) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k0 + k != 0) v[k0 + k] = cpk_cmul(v[k0 + k], w[2 * k], w[2 * k + 1]);
+}
+
 // Forward spectra staged by TMA: one thread issues a 16 KiB cp.async.bulk for X_{k+1} into a shared-memory
 // stage right after the exchange-1 barrier of transform k (every thread has consumed X_k by then); completion
 // is tracked by an mbarrier, and the conjugate code spectrum is fetched from TMEM before the wait.  No
@@ -339,11 +345,29 @@ __device__ __forceinline__ void tm_ld_wait16(float* r) {      // the registers b
                    "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]));
 }
 
+// The PRN's conjugate code spectrum of this thread (elements t + 128 j) in the order it is parked in TMEM.
+// Scalar form: (re, im) of j = 0..15.  Packed form: the transform reads it as the DATA of the first radix-16 stage
+// (the forward spectrum X supplies the "twiddles", see the kernel), i.e. (im, re) -- the swap of the swap-form
+// inverse -- in the order the radix-4 butterflies consume it: half H = j0 >> 1, position 4 (j0 & 1) + m <-> j = j0 + 4 m.
+template <bool PK>
+__device__ __forceinline__ void load_conjspec(float* w, const float2* cs) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float2 v = __ldg(cs + 128 * j);
+        if constexpr (PK) {
+            const int j0 = j & 3, m = j >> 2, q = 16 * (j0 >> 1) + 2 * (4 * (j0 & 1) + m);
+            w[q] = v.y; w[q + 1] = v.x;
+        } else {
+            w[2 * j] = v.x; w[2 * j + 1] = v.y;
+        }
+    }
+}
+
 // FFT: gr_fft2048t.cuh (exchange 1 in shared memory with 128-bit stores on a double-buffered 16 KiB buffer and
 // ONE block barrier per transform; exchange 2 + radix-8 through TMEM).  TM bit 1 / bit 2: stage-2 / stage-1
 // twiddles in TMEM (else registers).
 #define GR_ACQ_INV_SMEM (3 * GR_W_BUF1_BYTES)      // 2 x exchange-1 buffer + forward-spectrum stage = 48 KiB
-template <int G, int TM, int MINB>
+template <int G, int TM, int MINB, bool PK>
 __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const AcqArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* buf1 = reinterpret_cast<float4*>(smem_raw);                         // 2 x 16 KiB
@@ -377,7 +401,39 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
     if (t == 0) tma_load_1d(xs, spec, GR_N * 8, &xbar);
 
     cf tw1[(TM & 4) ? 1 : 16], tw2[(TM & 2) ? 1 : 16];
-    {
+    if constexpr (PK) {
+        // Packed form: every twiddle is applied on the INPUT side of the next stage, where it folds into the first
+        // layer of additions (gr_cpk.cuh).  Stage 2, thread (k1, n3): input n2 carries W_2048^((8 n2 + n3) k1);
+        // stage 3, thread (k1loc, k2 = k2lo + 8 h): input n3 of group h carries W_128^(n3 k2).
+        static_assert((TM & 6) == 6, "the packed form keeps both twiddle sets in TMEM");
+        float w[32];
+        const int L = t & 31;
+        const int k1 = 4 * (t >> 5) + 2 * (L >> 4) + (L & 1), n3 = (L >> 1) & 7;
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) {
+            const float2 u = a.tab.tw1[(8 * n2 + n3) * 16 + k1];
+            const int j0 = n2 & 3, m = n2 >> 2, q = 16 * (j0 >> 1) + 2 * (4 * (j0 & 1) + m);
+            w[q] = u.x; w[q + 1] = u.y;
+        }
+        tm_st16(tm + kColTw1, w);
+        tm_st16(tm + kColTw1 + 16, w + 16);
+        const int k2lo = 4 * ((L >> 2) & 1) + 2 * ((L >> 4) & 1) + ((L >> 1) & 1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int n = 1; n < 8; ++n) {
+                const float2 u = a.tab.tw2[n * 16 + k2lo + 8 * h];
+                w[16 * h + 2 * (n - 1)] = u.x; w[16 * h + 2 * (n - 1) + 1] = u.y;
+            }
+            w[16 * h + 14] = 0.f; w[16 * h + 15] = 0.f;
+        }
+        tm_st16(tm + kColTw2, w);
+        tm_st16(tm + kColTw2 + 16, w + 16);
+        load_conjspec<true>(w, a.tab.conjspec + (size_t)a.prns[grp * G] * GR_N + t);
+        tm_st16(tm + kColC, w);
+        tm_st16(tm + kColC + 16, w + 16);
+        tm_wait_st();
+    } else {
         float w[32];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -393,11 +449,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             if (!(TM & 2)) tw2[(TM & 2) ? 0 : i] = cf{u.x, u.y};
         }
         if (TM & 2) { tm_st16(tm + kColTw2, w); tm_st16(tm + kColTw2 + 16, w + 16); }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {                          // first job's conjugate code spectrum
-            const float2 v = __ldg(a.tab.conjspec + (size_t)a.prns[grp * G] * GR_N + t + 128 * j);
-            w[2 * j] = v.x; w[2 * j + 1] = v.y;
-        }
+        load_conjspec<false>(w, a.tab.conjspec + (size_t)a.prns[grp * G] * GR_N + t);     // first job's conjugate code spectrum
         tm_st16(tm + kColC, w);
         tm_st16(tm + kColC + 16, w + 16);
         tm_wait_st();
@@ -413,6 +465,68 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = 0.f;
         for (int k = 0; k < a.nnoncoh; ++k) {
+          if constexpr (PK) {
+            // packed form: one 64-bit register pair per complex value, FADD2 / FMUL2 / FFMA2 (gr_cpk.cuh).
+            // Stage 1 computes the radix-16 butterflies of (Im Y, Re Y), Y_j = X_j conj(C_j), as "data = (C.im, C.re),
+            // twiddle = conj(X_j)": the spectrum product folds into the first layer of additions like a twiddle.
+            cpk y[16];
+            float cl[16], ch[16];
+            tm_ld16_issue(tm + kColC, cl);
+            tm_ld16_issue(tm + kColC + 16, ch);
+            mbar_wait(&xbar, par);
+            float xl[16], xh[16];                                // conj(X_j) in butterfly order, as the data above
+#pragma unroll
+            for (int m2 = 0; m2 < 8; ++m2) {
+                const float4 v = xs[128 * m2 + t];               // elements j = 2 m2, 2 m2 + 1
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 2 * m2 + e, j0 = j & 3, m = j >> 2, q = 2 * (4 * (j0 & 1) + m);
+                    const float re = e ? v.z : v.x, im = e ? v.w : v.y;
+                    if (j0 >> 1) { xh[q] = re; xh[q + 1] = -im; } else { xl[q] = re; xl[q + 1] = -im; }
+                }
+            }
+            tm_ld_wait16(cl);
+            tm_ld_wait16(ch);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int j0 = j & 3, m = j >> 2, q = 2 * (4 * (j0 & 1) + m);
+                y[j] = (j0 >> 1) ? cpk_make(ch[q], ch[q + 1]) : cpk_make(cl[q], cl[q + 1]);
+            }
+            cpk_dft16_in_tw<0>(y, xl);
+            cpk_dft16_in_tw<2>(y, xh);
+            cpk_dft16_out(y);
+            float4* b1 = buf1 + par * (GR_W_BUF1_BYTES / 16);
+            par ^= 1;
+            fftt_ex1_write_pk(b1, t, y);
+            float wa[16], wb[16];
+            tm_ld16_issue(tm + kColTw1, wa);                     // arrives while the block waits at the barrier
+            __syncthreads();
+            if (t == 0) {                                        // every thread has consumed X_k: refill the stage
+                if (k + 1 < a.nnoncoh) {
+                    tma_load_1d(xs, spec + (size_t)(k + 1) * (GR_N * 8), GR_N * 8, &xbar);
+                } else {                                         // first spectrum of the next job (same bin or next work item)
+                    int nw = work;
+                    if (g + 1 >= G || grp * G + g + 1 >= a.nprn) nw += gridDim.x;
+                    if (nw < nwork) tma_load_1d(xs, reinterpret_cast<const char*>(a.spec) + (size_t)(nw / a.ngroups) * spec_stride,
+                                                GR_N * 8, &xbar);
+                }
+            }
+            fftt_ex1_read_pk(b1, t, y);
+            tm_ld_wait16(wa);
+            tm_ld16_issue(tm + kColTw1 + 16, wb);
+            cpk_dft16_in_tw<0>(y, wa);
+            tm_ld_wait16(wb);
+            cpk_dft16_in_tw<2>(y, wb);
+            cpk_dft16_out(y);
+            fftt_ex2_stage3_pk(tm + kColX, tm + kColTw2, y);
+            if (a.mode == GR_ACQ_POW) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { float yr, yi; cpk_split(y[j], yr, yi); acc[j] = fmaf(yr, yr, fmaf(yi, yi, acc[j])); }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { float yr, yi; cpk_split(y[j], yr, yi); acc[j] += sqrtf(yr * yr + yi * yi); }
+            }
+          } else {
             cf y[16];
             float w0[16], w1[16];
             tm_ld16_issue(tm + kColC, w0);
@@ -485,6 +599,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc[j] += sqrtf(y[j].x * y[j].x + y[j].y * y[j].y);
             }
+          }
         }
         // the job after this one; its conjugate spectrum is loaded now: L2 latency hidden behind the cell reduction
         int n_work = work, n_g = g + 1;
@@ -492,14 +607,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
         const bool has_next = n_work < nwork;
         const int n_grp = n_work % a.ngroups;
         float w[32];
-        if (has_next) {
-            const float2* cs = a.tab.conjspec + (size_t)a.prns[n_grp * G + n_g] * GR_N + t;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float2 v = __ldg(cs + 128 * j);
-                w[2 * j] = v.x; w[2 * j + 1] = v.y;
-            }
-        }
+        if (has_next) load_conjspec<PK>(w, a.tab.conjspec + (size_t)a.prns[n_grp * G + n_g] * GR_N + t);
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] *= sc;
         acq_cell_epilogue(acc, obase, t, a.out + ((size_t)rec * a.nprn + grp * G + g) * a.nbins + bin, &scratch);
@@ -594,7 +702,9 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
     const bool one = p->tcoh == 1;
     void (*fwd)(const AcqArgs) = p->in_format == GR_IN_U8IQ ? (one ? acq_fwd_kernel<GR_IN_U8IQ, true> : acq_fwd_kernel<GR_IN_U8IQ, false>)
                                                             : (one ? acq_fwd_kernel<GR_IN_CF32, true> : acq_fwd_kernel<GR_IN_CF32, false>);
-    void (*inv)(const AcqArgs) = acq_inv_kernel<GR_ACQ_G, 6, 4>;
+    // development switch: GPSB200_ACQ_SCALAR=1 selects the scalar-FP32 form of the same transform (A/B timing)
+    static const bool scalar_fp = getenv("GPSB200_ACQ_SCALAR") != nullptr;
+    void (*inv)(const AcqArgs) = scalar_fp ? acq_inv_kernel<GR_ACQ_G, 6, 4, false> : acq_inv_kernel<GR_ACQ_G, 6, 4, true>;
     const size_t fwd_smem = GR_FFT_SMEM_BYTES + (one ? 0 : (size_t)p->tcoh * sizeof(cf));
     if (fwd_smem > 200 * 1024) { gr_set_error("gr_acq_run_dev: tcoh too large"); return GR_ERR_ARG; }
     GR_CUDA(cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));

@@ -22,6 +22,7 @@
 // Output registers: v[j] = X[ fftt_out_base(t) + 128 j ].
 #pragma once
 #include "gr_fft2048w.cuh"
+#include "gr_cpk.cuh"
 
 // residue (mod 128) of the output indices held by thread t:  k1 + 16 (k2 & 7)
 GR_HD int fftt_out_base(int t) {
@@ -100,6 +101,67 @@ __device__ __forceinline__ void fftt_ex2_stage3(uint32_t taddr, cf* v) {
     }
     dft8(a);
     dft8(b);
+#pragma unroll
+    for (int k3 = 0; k3 < 8; ++k3) {
+        v[2 * k3] = a[k3];
+        v[2 * k3 + 1] = b[k3];
+    }
+}
+
+// ---- the same transform on packed complex registers (gr_cpk.cuh: FADD2 / FMUL2 / FFMA2) ----
+__device__ __forceinline__ void fftt_ex1_write_pk(float4* buf1, int t, const cpk* v) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        float4 q;
+        cpk_split(v[2 * m], q.x, q.y);
+        cpk_split(v[2 * m + 1], q.z, q.w);
+        buf1[m * 128 + t] = q;
+    }
+}
+__device__ __forceinline__ void fftt_ex1_read_pk(const float4* buf1, int t, cpk* v) {
+    const int w = t >> 5, L = t & 31;
+    const cpk* b = reinterpret_cast<const cpk*>(buf1) + (2 * w + (L >> 4)) * 256 + (L & 15);
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = b[16 * n2];
+}
+// Exchange 2 + stage 3 with the stage-2 twiddles W_128^(n3 k2) applied on the input side of the two radix-8 groups
+// (tw_addr: 2 x 16 TMEM columns, 7 twiddles per group, fetched behind the second round's loads).
+__device__ __forceinline__ void fftt_ex2_stage3_pk(uint32_t taddr, uint32_t tw_addr, cpk* v) {
+    float r[32];
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+        const int K = 8 * ((k2 >> 2) & 1) + 4 * ((k2 >> 1) & 1) + 2 * ((k2 >> 3) & 1) + (k2 & 1);   // (e2 e1 e3 e0)
+        cpk_split(v[k2], r[2 * K], r[2 * K + 1]);
+    }
+    tm_round(taddr, r);
+    tm_st_16x256b_x4(taddr, r);
+    tm_st_16x256b_x4(taddr + (16u << 16), r + 16);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    float wa[16], wb[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%64];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%65];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47}, [%66];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%67];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]),
+          "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]), "=f"(r[17]), "=f"(r[18]),
+          "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]),
+          "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31]),
+          "=f"(wa[0]), "=f"(wa[1]), "=f"(wa[2]), "=f"(wa[3]), "=f"(wa[4]), "=f"(wa[5]), "=f"(wa[6]), "=f"(wa[7]), "=f"(wa[8]),
+          "=f"(wa[9]), "=f"(wa[10]), "=f"(wa[11]), "=f"(wa[12]), "=f"(wa[13]), "=f"(wa[14]), "=f"(wa[15]),
+          "=f"(wb[0]), "=f"(wb[1]), "=f"(wb[2]), "=f"(wb[3]), "=f"(wb[4]), "=f"(wb[5]), "=f"(wb[6]), "=f"(wb[7]), "=f"(wb[8]),
+          "=f"(wb[9]), "=f"(wb[10]), "=f"(wb[11]), "=f"(wb[12]), "=f"(wb[13]), "=f"(wb[14]), "=f"(wb[15])
+        : "r"(taddr), "r"(taddr + 16), "r"(tw_addr), "r"(tw_addr + 16));
+    cpk a[8], b[8];
+#pragma unroll
+    for (int n3 = 0; n3 < 8; ++n3) {
+        const int K = 4 * (n3 & 1) + 2 * (n3 >> 2) + ((n3 >> 1) & 1);
+        a[n3] = cpk_make(r[2 * K], r[2 * K + 1]);
+        b[n3] = cpk_make(r[2 * (8 + K)], r[2 * (8 + K) + 1]);
+    }
+    cpk_dft8_tw(a, wa);
+    cpk_dft8_tw(b, wb);
 #pragma unroll
     for (int k3 = 0; k3 < 8; ++k3) {
         v[2 * k3] = a[k3];
