@@ -75,49 +75,6 @@ __device__ __forceinline__ float nco_arg(float w32, long long n) {
     return __fmul_rn(w32, tsec);
 }
 
-struct BlockStat {
-    double sum, sum2;
-    float mx;
-    int idx;
-};
-
-// CTA-wide statistics of 2048 values held 16 per thread (value j of this thread = lag nb + 128 j).
-// One barrier; every thread gets the result.  sh_* are 4-entry scratch arrays that the caller must not
-// reuse before its next block barrier.
-__device__ __forceinline__ BlockStat block_stats(const float* st, int nb, int t, double* sh_d, float* sh_f, int* sh_i) {
-    float s = 0.f, s2 = 0.f, mx = -1.f;
-    int idx = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float v = st[j];
-        s += v;
-        s2 = fmaf(v, v, s2);
-        if (v > mx) { mx = v; idx = nb + 128 * j; }
-    }
-    double ds = (double)s, ds2 = (double)s2;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ds += __shfl_xor_sync(0xffffffffu, ds, o);
-        ds2 += __shfl_xor_sync(0xffffffffu, ds2, o);
-        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (om > mx || (om == mx && oi < idx)) { mx = om; idx = oi; }
-    }
-    const int w = t >> 5;
-    if ((t & 31) == 0) { sh_d[w] = ds; sh_d[4 + w] = ds2; sh_f[w] = mx; sh_i[w] = idx; }
-    __syncthreads();
-    BlockStat r{0.0, 0.0, -1.f, 0};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        r.sum += sh_d[k];
-        r.sum2 += sh_d[4 + k];
-        const float om = sh_f[k];
-        const int oi = sh_i[k];
-        if (om > r.mx || (om == r.mx && oi < r.idx)) { r.mx = om; r.idx = oi; }
-    }
-    return r;
-}
-
 // ---- kernel 1: forward spectra ------------------------------------------------------------------
 // CTA = (recording, non-coherent interval, chunk of Doppler bins); it loops over its bins with the FFT
 // twiddles (and, for tcoh = 1, the 16 samples per thread) held in registers: wipe-off, time-domain fold of
@@ -213,41 +170,81 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
 
 // reduce one PRN's 2048 scaled lags (st[j] = lag nb + 128 j; nb = fftt_out_base(t)) to its gr_acq_cell.
 // Two block barriers; the scratch arrays are free again after the caller's next block barrier.
+// Per-(PRN, bin) reduction of the 2048 accumulated lags (16 per thread: value j = lag nb + 128 j) to one cell:
+// mean, population std, first maximum, largest value farther than GR_SECOND_PEAK_GUARD lags from it, and the
+// maximum's two neighbours.  Two block barriers.  It runs once per 10-20 transforms, but as a plain
+// per-lag loop it was a fifth of the kernel's warp time (ncu), so it is written for instruction count:
+//  * sums: float per thread and per warp (tree), double only across the four warps;
+//  * arg-max: values are >= 0, so their bit patterns order like unsigned integers: two REDUX per warp
+//    (max of the patterns, then min of the lags that hold it = first maximum) instead of five shuffle rounds;
+//  * second peak: a thread's lags are 128 apart, so at most ONE of them lies in the guard window of the
+//    maximum; with the thread's two largest values tracked in the first pass the answer is O(1) per thread;
+//  * neighbours: only the two threads that own lags mx -/+ 1 select them.
 struct AcqScratch {
     double d[8];
     float f[4];
     int i[4];
     float sec[4];
 };
+__device__ __forceinline__ float sel16(const float* st, int j) {
+    float v = st[0];
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v = (j == q) ? st[q] : v;
+    return v;
+}
 __device__ __forceinline__ void acq_cell_epilogue(const float* st, int nb, int t, gr_acq_cell* cell, AcqScratch* S) {
-    const BlockStat bs = block_stats(st, nb, t, S->d, S->f, S->i);
-    const int mx = bs.idx;
-    const int lo = (mx + GR_N - 1) & (GR_N - 1), hi = (mx + 1) & (GR_N - 1);
-    float sec = -1.f;
+    float s = 0.f, s2 = 0.f, m1 = -1.f, m2 = -1.f;
+    int j1 = 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const int n = nb + 128 * j;
-        int d = n - mx;
-        d = d < 0 ? -d : d;
-        d = d > GR_N / 2 ? GR_N - d : d;
-        if (d > GR_SECOND_PEAK_GUARD) sec = fmaxf(sec, st[j]);
-        if (n == lo) cell->em1 = st[j];
-        if (n == hi) cell->ep1 = st[j];
+        const float v = st[j];
+        s += v;
+        s2 = fmaf(v, v, s2);
+        const bool gt = v > m1;                     // strict: the first of equal values stays the maximum
+        m2 = gt ? m1 : fmaxf(m2, v);
+        j1 = gt ? j : j1;
+        m1 = gt ? v : m1;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sec = fmaxf(sec, __shfl_xor_sync(0xffffffffu, sec, o));
-    if ((t & 31) == 0) S->sec[t >> 5] = sec;
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(m1));
+    const int widx = (int)__reduce_min_sync(0xffffffffu, __float_as_uint(m1) == wmax ? (unsigned)(nb + 128 * j1) : 0x7fffffffu);
+    const int w = t >> 5;
+    if ((t & 31) == 0) { S->d[w] = (double)s; S->d[4 + w] = (double)s2; S->f[w] = __uint_as_float(wmax); S->i[w] = widx; }
+    __syncthreads();
+    float peak = S->f[0];
+    int mx = S->i[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        const float om = S->f[k];
+        const int oi = S->i[k];
+        if (om > peak || (om == peak && oi < mx)) { peak = om; mx = oi; }
+    }
+    // the one lag of this thread that can lie inside [mx - G, mx + G] (circular)
+    const int r = (mx - GR_SECOND_PEAK_GUARD - nb) & (GR_N - 1);
+    const int jc = ((r + 127) >> 7) & 15;
+    const bool inside = ((nb + 128 * jc - (mx - GR_SECOND_PEAK_GUARD)) & (GR_N - 1)) <= 2 * GR_SECOND_PEAK_GUARD;
+    float sec = (inside && jc == j1) ? m2 : m1;
+    sec = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(sec, 0.f))));
+    if ((t & 31) == 0) S->sec[w] = sec;
+    const int lo = (mx + GR_N - 1) & (GR_N - 1), hi = (mx + 1) & (GR_N - 1);
+    if (((lo - nb) & 127) == 0) cell->em1 = sel16(st, ((lo - nb) & (GR_N - 1)) >> 7);
+    if (((hi - nb) & 127) == 0) cell->ep1 = sel16(st, ((hi - nb) & (GR_N - 1)) >> 7);
     __syncthreads();
     if (t == 0) {
-        const double mean = bs.sum / GR_N;
-        double var = bs.sum2 / GR_N - mean * mean;
+        const double sum = (S->d[0] + S->d[1]) + (S->d[2] + S->d[3]), sum2 = (S->d[4] + S->d[5]) + (S->d[6] + S->d[7]);
+        const double mean = sum * (1.0 / GR_N);
+        double var = sum2 * (1.0 / GR_N) - mean * mean;
         var = var > 0.0 ? var : 0.0;
-        const double sd = sqrt(var);
+        const float sd = sqrtf((float)var);          // float sqrt / divide: the double versions are ~500 cycles of one thread
         cell->mx = mx;
-        cell->peak = bs.mx;
+        cell->peak = peak;
         cell->mean = (float)mean;
-        cell->std = (float)sd;
-        cell->z = (float)(((double)bs.mx - mean) / sd);
+        cell->std = sd;
+        cell->z = (float)((double)peak - mean) / sd;
         cell->second = fmaxf(fmaxf(S->sec[0], S->sec[1]), fmaxf(S->sec[2], S->sec[3]));
     }
 }
