@@ -705,7 +705,10 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
     const size_t fwd_smem = GR_FFT_SMEM_BYTES + (one ? 0 : (size_t)p->tcoh * sizeof(cf));
     if (fwd_smem > 200 * 1024) { gr_set_error("gr_acq_run_dev: tcoh too large"); return GR_ERR_ARG; }
     GR_CUDA(cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
-    GR_CUDA(cudaFuncSetAttribute(inv, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_ACQ_INV_SMEM));
+    // development switch: GPSB200_ACQ_CTAS=2|3 pads the dynamic shared memory so that fewer CTAs fit an SM (occupancy study)
+    static const int ctas_per_sm = getenv("GPSB200_ACQ_CTAS") ? atoi(getenv("GPSB200_ACQ_CTAS")) : 4;
+    const int inv_smem = ctas_per_sm == 3 ? 72 * 1024 : ctas_per_sm == 2 ? 110 * 1024 : ctas_per_sm == 1 ? 200 * 1024 : GR_ACQ_INV_SMEM;
+    GR_CUDA(cudaFuncSetAttribute(inv, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem));
     const size_t bps = p->in_format == GR_IN_U8IQ ? 2 : 8;
     p->last_launches = 0;
     for (int r0 = 0; r0 < nrec; r0 += sub) {
@@ -737,8 +740,9 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         const long long ninv = (long long)nr * p->nbins * a.ngroups;
         if (nfwd > 0x7fffffffLL || ninv > 0x7fffffffLL) { gr_set_error("gr_acq_run_dev: grid too large"); return GR_ERR_ARG; }
         fwd<<<(unsigned)nfwd, GR_FFT_THREADS, fwd_smem, s>>>(a);
-        const long long ninv_grid = ninv < 4LL * gr_lib()->num_sms ? ninv : 4LL * gr_lib()->num_sms;
-        inv<<<(unsigned)ninv_grid, GR_FFT_THREADS, GR_ACQ_INV_SMEM, s>>>(a);
+        const long long resident = (long long)(ctas_per_sm >= 1 && ctas_per_sm <= 4 ? ctas_per_sm : 4) * gr_lib()->num_sms;
+        const long long ninv_grid = ninv < resident ? ninv : resident;
+        inv<<<(unsigned)ninv_grid, GR_FFT_THREADS, inv_smem, s>>>(a);
         GR_CUDA(cudaGetLastError());
         p->last_launches += 2;
     }
