@@ -234,7 +234,7 @@ __device__ __forceinline__ void acq_cell_epilogue(const float* st, int nb, int t
     if (((lo - nb) & 127) == 0) cell->em1 = sel16(st, ((lo - nb) & (GR_N - 1)) >> 7);
     if (((hi - nb) & 127) == 0) cell->ep1 = sel16(st, ((hi - nb) & (GR_N - 1)) >> 7);
     __syncthreads();
-    if (t == 0) {
+    if (t == 64) {                                   // not warp 0: that one issues the TMA loads
         const double sum = (S->d[0] + S->d[1]) + (S->d[2] + S->d[3]), sum2 = (S->d[4] + S->d[5]) + (S->d[6] + S->d[7]);
         const double mean = sum * (1.0 / GR_N);
         double var = sum2 * (1.0 / GR_N) - mean * mean;
@@ -328,6 +328,13 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
 }
+// one lane of a converged warp (the pattern that keeps a TMA issue in the uniform datapath: behind `if (t == 0)` the
+// compiler wraps the bulk copy into a leader-election loop and the issuing warp falls ~300 cycles behind its CTA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+    return p != 0;
+}
 // c[] fetch split into issue and wait so that the X wait sits in between
 __device__ __forceinline__ void tm_ld16_issue(uint32_t taddr, float* r) {
     asm volatile(
@@ -377,6 +384,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
     constexpr int kColC = 0, kColX = 32, kColTw2 = 64, kColTw1 = kColTw2 + ((TM & 2) ? 32 : 0);
 
     const int t = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);       // warp-uniform for the compiler
     const int nwork = a.nrec * a.nbins * a.ngroups;
     int work = blockIdx.x;                                     // host guarantees gridDim.x <= nwork
 
@@ -395,7 +403,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
     int grp = work % a.ngroups, bin = (work / a.ngroups) % a.nbins, rec = work / (a.ngroups * a.nbins);
     const size_t spec_stride = (size_t)a.nnoncoh * GR_N * 8;                     // bytes per (recording, bin)
     const char* spec = reinterpret_cast<const char*>(a.spec) + (size_t)(work / a.ngroups) * spec_stride;
-    if (t == 0) tma_load_1d(xs, spec, GR_N * 8, &xbar);
+    if (warp == 0 && elect_one()) tma_load_1d(xs, spec, GR_N * 8, &xbar);
 
     cf tw1[(TM & 4) ? 1 : 16], tw2[(TM & 2) ? 1 : 16];
     if constexpr (PK) {
@@ -458,6 +466,13 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
     int g = 0;
 
     while (true) {
+        // first spectrum of the job after this one (same bin or next work item); fetched during this job's last transform
+        const char* xjob_next;
+        {
+            int nw = work;
+            if (g + 1 >= G || grp * G + g + 1 >= a.nprn) nw += gridDim.x;
+            xjob_next = nw < nwork ? reinterpret_cast<const char*>(a.spec) + (size_t)(nw / a.ngroups) * spec_stride : nullptr;
+        }
         float acc[16];                                          // non-coherent accumulators, 16 lags per thread
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = 0.f;
@@ -498,15 +513,9 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             float wa[16], wb[16];
             tm_ld16_issue(tm + kColTw1, wa);                     // arrives while the block waits at the barrier
             __syncthreads();
-            if (t == 0) {                                        // every thread has consumed X_k: refill the stage
-                if (k + 1 < a.nnoncoh) {
-                    tma_load_1d(xs, spec + (size_t)(k + 1) * (GR_N * 8), GR_N * 8, &xbar);
-                } else {                                         // first spectrum of the next job (same bin or next work item)
-                    int nw = work;
-                    if (g + 1 >= G || grp * G + g + 1 >= a.nprn) nw += gridDim.x;
-                    if (nw < nwork) tma_load_1d(xs, reinterpret_cast<const char*>(a.spec) + (size_t)(nw / a.ngroups) * spec_stride,
-                                                GR_N * 8, &xbar);
-                }
+            {                                                    // every thread has consumed X_k: refill the stage
+                const char* src = (k + 1 < a.nnoncoh) ? spec + (size_t)(k + 1) * (GR_N * 8) : xjob_next;
+                if (warp == 0 && src != nullptr && elect_one()) tma_load_1d(xs, src, GR_N * 8, &xbar);
             }
             fftt_ex1_read_pk(b1, t, y);
             tm_ld_wait16(wa);
@@ -566,15 +575,9 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             fftw_ex1_write(b1, t, y);
             if (TM & 2) tm_ld16_issue(tm + kColTw2, wa);         // arrives while the block waits at the barrier
             __syncthreads();
-            if (t == 0) {                                        // every thread has consumed X_k: refill the stage
-                if (k + 1 < a.nnoncoh) {
-                    tma_load_1d(xs, spec + (size_t)(k + 1) * (GR_N * 8), GR_N * 8, &xbar);
-                } else {                                         // first spectrum of the next job (same bin or next work item)
-                    int nw = work;
-                    if (g + 1 >= G || grp * G + g + 1 >= a.nprn) nw += gridDim.x;
-                    if (nw < nwork) tma_load_1d(xs, reinterpret_cast<const char*>(a.spec) + (size_t)(nw / a.ngroups) * spec_stride,
-                                                GR_N * 8, &xbar);
-                }
+            {                                                    // every thread has consumed X_k: refill the stage
+                const char* src = (k + 1 < a.nnoncoh) ? spec + (size_t)(k + 1) * (GR_N * 8) : xjob_next;
+                if (warp == 0 && src != nullptr && elect_one()) tma_load_1d(xs, src, GR_N * 8, &xbar);
             }
             fftt_ex1_read(b1, t, y);
             dft16(y);
