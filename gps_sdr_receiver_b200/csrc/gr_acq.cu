@@ -25,8 +25,11 @@
 
 struct gr_acq_plan {
     int nprn, nbins, tcoh, nnoncoh, mode, in_format;
+    int nbase;             // distinct forward spectra per (recording, interval): bins 1 kHz apart share one, see gr_acq_plan_create
     int32_t* d_prns;
-    float* d_w32;          // fl32(2*pi*f) per bin (python-float product rounded once, gpsrecv.py:233)
+    float* d_w32;          // fl32(2*pi*f) per BASE bin (python-float product rounded once, gpsrecv.py:233)
+    int32_t* d_bin_base;   // [nbins] base spectrum of a bin
+    int32_t* d_bin_shift;  // [nbins] its circular shift in FFT bins, 0..2047
     // staging for the host entry point
     void* d_in;  size_t in_bytes;
     gr_acq_cell* d_out; size_t out_bytes;
@@ -41,12 +44,14 @@ struct AcqArgs {
     const void* samples;
     long long rec_stride;      // samples
     const int32_t* prns;
-    const float* w32;
-    int nrec, nprn, nbins, ngroups, tcoh, nnoncoh, mode;
-    int nchunks, bins_per_chunk;   // forward kernel: Doppler bins per CTA
+    const float* w32;          // per base bin
+    const int32_t* bin_base;   // per bin: base spectrum, circular shift (FFT bins)
+    const int32_t* bin_shift;
+    int nrec, nprn, nbins, nbase, ngroups, tcoh, nnoncoh, mode;
+    int nchunks, bins_per_chunk;   // forward kernel: base bins per CTA
     float scale;               // 1 / (tcoh * 2048)
     gr_acq_cell* out;
-    float2* spec;              // scratch: forward spectra [nrec][nbins][nnoncoh][8][128][2] (paired layout)
+    float2* spec;              // scratch: forward spectra [nrec][nbase][nnoncoh][2][2048]: natural order, and shifted by one bin
     GrTables tab;
 };
 
@@ -101,7 +106,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
     const int k = id % a.nnoncoh;
     const int rec = id / a.nnoncoh;
     const int bin0 = chunk * a.bins_per_chunk;
-    const int bin1 = min(a.nbins, bin0 + a.bins_per_chunk);
+    const int bin1 = min(a.nbase, bin0 + a.bins_per_chunk);
 
     cf tw1[16], tw2[16];
 #pragma unroll
@@ -161,9 +166,15 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
             for (int j = 0; j < 16; ++j) X[j] = cmul(X[j], nco_fast(nco_arg(w32, base0 + 128 * j)));
         }
         fft2048<true>(X, smem, tw1, tw2, t);
-        float4* d4 = reinterpret_cast<float4*>(a.spec + ((size_t)(rec * a.nbins + bin) * a.nnoncoh + k) * GR_N);
+        // two copies in natural order, E0[m] = X[m] and E1[m] = X[m + 1]: the inverse kernel fetches a spectrum rotated by
+        // any number of bins with 16-byte aligned bulk copies (even rotations of E0, odd ones as even rotations of E1)
+        float2* e0 = a.spec + ((size_t)(rec * a.nbase + bin) * a.nnoncoh + k) * (2 * GR_N);
 #pragma unroll
-        for (int m = 0; m < 8; ++m) d4[m * 128 + t] = make_float4(X[2 * m].x, X[2 * m].y, X[2 * m + 1].x, X[2 * m + 1].y);
+        for (int j = 0; j < 16; ++j) {
+            const float2 v = make_float2(X[j].x, X[j].y);
+            e0[t + 128 * j] = v;
+            e0[GR_N + ((t + 128 * j + GR_N - 1) & (GR_N - 1))] = v;
+        }
         __syncthreads();                                           // the FFT buffers (and Rtab) are reused by the next bin
     }
 }
@@ -328,6 +339,17 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
 }
+// stage[m] = E[(m + rot) mod 2048] for an even rotation: one or two bulk copies completing on one mbarrier phase
+__device__ __forceinline__ void tma_load_rot(void* stage, const char* E, int rot, uint64_t* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), dst = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t head = (uint32_t)(GR_N - rot) * 8u, tail = (uint32_t)rot * 8u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"((uint32_t)(GR_N * 8)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(E + tail), "r"(head), "r"(b) : "memory");
+    if (rot)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + head), "l"(E), "r"(tail), "r"(b) : "memory");
+}
 // one lane of a converged warp (the pattern that keeps a TMA issue in the uniform datapath: behind `if (t == 0)` the
 // compiler wraps the bulk copy into a leader-election loop and the issuing warp falls ~300 cycles behind its CTA)
 __device__ __forceinline__ bool elect_one() {
@@ -375,7 +397,7 @@ template <int G, int TM, int MINB, bool PK>
 __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const AcqArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* buf1 = reinterpret_cast<float4*>(smem_raw);                         // 2 x 16 KiB
-    float4* xs = reinterpret_cast<float4*>(smem_raw + 2 * GR_W_BUF1_BYTES);      // forward-spectrum stage, 16 KiB
+    const float2* xs = reinterpret_cast<const float2*>(smem_raw + 2 * GR_W_BUF1_BYTES);  // forward-spectrum stage, 16 KiB, natural order
     __shared__ __align__(8) uint64_t xbar;
     __shared__ AcqScratch scratch;
     __shared__ uint32_t tm_base_sh;
@@ -401,9 +423,19 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
 
     // work item -> (recording, bin, group); PRN groups fastest
     int grp = work % a.ngroups, bin = (work / a.ngroups) % a.nbins, rec = work / (a.ngroups * a.nbins);
-    const size_t spec_stride = (size_t)a.nnoncoh * GR_N * 8;                     // bytes per (recording, bin)
-    const char* spec = reinterpret_cast<const char*>(a.spec) + (size_t)(work / a.ngroups) * spec_stride;
-    if (warp == 0 && elect_one()) tma_load_1d(xs, spec, GR_N * 8, &xbar);
+    // The spectrum of (recording, bin, interval k) is the base spectrum of the bin's 1-kHz class rotated by the bin's
+    // shift: copy (shift & 1) of the pair the forward kernel wrote, rotated by the even part (tma_load_rot).
+    constexpr size_t kStrideK = 2 * (size_t)GR_N * 8;                            // bytes between intervals
+    auto item_src = [&](int wk, int& rot_out) -> const char* {
+        const int b = (wk / a.ngroups) % a.nbins, r = wk / (a.ngroups * a.nbins);
+        const int sh = a.bin_shift[b];
+        rot_out = sh & ~1;
+        return reinterpret_cast<const char*>(a.spec) + ((size_t)(r * a.nbase + a.bin_base[b]) * a.nnoncoh * 2 + (sh & 1)) * (GR_N * 8);
+    };
+    int rot;
+    const char* spec = item_src(work, rot);
+    void* xstage = smem_raw + 2 * GR_W_BUF1_BYTES;
+    if (warp == 0 && elect_one()) tma_load_rot(xstage, spec, rot, &xbar);
 
     cf tw1[(TM & 4) ? 1 : 16], tw2[(TM & 2) ? 1 : 16];
     if constexpr (PK) {
@@ -467,12 +499,9 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
 
     while (true) {
         // first spectrum of the job after this one (same bin or next work item); fetched during this job's last transform
-        const char* xjob_next;
-        {
-            int nw = work;
-            if (g + 1 >= G || grp * G + g + 1 >= a.nprn) nw += gridDim.x;
-            xjob_next = nw < nwork ? reinterpret_cast<const char*>(a.spec) + (size_t)(nw / a.ngroups) * spec_stride : nullptr;
-        }
+        const char* xjob_next = spec;
+        int rot_next = rot;
+        if (g + 1 >= G || grp * G + g + 1 >= a.nprn) xjob_next = work + (int)gridDim.x < nwork ? item_src(work + gridDim.x, rot_next) : nullptr;
         float acc[16];                                          // non-coherent accumulators, 16 lags per thread
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = 0.f;
@@ -488,14 +517,10 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             mbar_wait(&xbar, par);
             float xl[16], xh[16];                                // conj(X_j) in butterfly order, as the data above
 #pragma unroll
-            for (int m2 = 0; m2 < 8; ++m2) {
-                const float4 v = xs[128 * m2 + t];               // elements j = 2 m2, 2 m2 + 1
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int j = 2 * m2 + e, j0 = j & 3, m = j >> 2, q = 2 * (4 * (j0 & 1) + m);
-                    const float re = e ? v.z : v.x, im = e ? v.w : v.y;
-                    if (j0 >> 1) { xh[q] = re; xh[q + 1] = -im; } else { xl[q] = re; xl[q + 1] = -im; }
-                }
+            for (int j = 0; j < 16; ++j) {
+                const float2 v = xs[t + 128 * j];
+                const int j0 = j & 3, m = j >> 2, q = 2 * (4 * (j0 & 1) + m);
+                if (j0 >> 1) { xh[q] = v.x; xh[q + 1] = -v.y; } else { xl[q] = v.x; xl[q + 1] = -v.y; }
             }
             tm_ld_wait16(cl);
             tm_ld_wait16(ch);
@@ -514,8 +539,9 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             tm_ld16_issue(tm + kColTw1, wa);                     // arrives while the block waits at the barrier
             __syncthreads();
             {                                                    // every thread has consumed X_k: refill the stage
-                const char* src = (k + 1 < a.nnoncoh) ? spec + (size_t)(k + 1) * (GR_N * 8) : xjob_next;
-                if (warp == 0 && src != nullptr && elect_one()) tma_load_1d(xs, src, GR_N * 8, &xbar);
+                const bool more = k + 1 < a.nnoncoh;
+                const char* src = more ? spec + (size_t)(k + 1) * kStrideK : xjob_next;
+                if (warp == 0 && src != nullptr && elect_one()) tma_load_rot(xstage, src, more ? rot : rot_next, &xbar);
             }
             fftt_ex1_read_pk(b1, t, y);
             tm_ld_wait16(wa);
@@ -539,11 +565,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             tm_ld16_issue(tm + kColC + 16, w1);
             mbar_wait(&xbar, par);
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const float4 v = xs[128 * m + t];
-                y[2 * m] = cf{v.x, v.y};
-                y[2 * m + 1] = cf{v.z, v.w};
-            }
+            for (int j = 0; j < 16; ++j) { const float2 v = xs[t + 128 * j]; y[j] = cf{v.x, v.y}; }
             tm_ld_wait16(w0);
             tm_ld_wait16(w1);
 #pragma unroll
@@ -576,8 +598,9 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             if (TM & 2) tm_ld16_issue(tm + kColTw2, wa);         // arrives while the block waits at the barrier
             __syncthreads();
             {                                                    // every thread has consumed X_k: refill the stage
-                const char* src = (k + 1 < a.nnoncoh) ? spec + (size_t)(k + 1) * (GR_N * 8) : xjob_next;
-                if (warp == 0 && src != nullptr && elect_one()) tma_load_1d(xs, src, GR_N * 8, &xbar);
+                const bool more = k + 1 < a.nnoncoh;
+                const char* src = more ? spec + (size_t)(k + 1) * kStrideK : xjob_next;
+                if (warp == 0 && src != nullptr && elect_one()) tma_load_rot(xstage, src, more ? rot : rot_next, &xbar);
             }
             fftt_ex1_read(b1, t, y);
             dft16(y);
@@ -617,7 +640,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
         tm_wait_st();
         if (n_work != work) {
             work = n_work; grp = n_grp; bin = (work / a.ngroups) % a.nbins; rec = work / (a.ngroups * a.nbins);
-            spec = reinterpret_cast<const char*>(a.spec) + (size_t)(work / a.ngroups) * spec_stride;
+            spec = xjob_next; rot = rot_next;
         }
         g = n_g;
     }
@@ -645,13 +668,40 @@ extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* b
     p->d_in = nullptr; p->in_bytes = 0; p->d_out = nullptr; p->out_bytes = 0; p->last_launches = 0;
     p->d_cells = nullptr; p->cells_bytes = 0; p->d_best = nullptr; p->best_bytes = 0;
     p->d_spec = nullptr; p->spec_bytes = 0;
-    std::vector<float> w(nbins);
-    for (int b = 0; b < nbins; ++b) w[b] = (float)(2.0 * 3.141592653589793 * bin_hz[b]);   // 2*np.pi*freq, then weak -> float32
+    // Bins whose frequencies differ by a multiple of fs / 2048 = 1 kHz share ONE forward spectrum: the wipe-off factor
+    // exp(-i 2 pi q 1000 (n + 1) / fs) = exp(-i 2 pi q (n + 1) / 2048) is the same in every 1-ms block, so it commutes with
+    // the coherent fold and turns into a circular shift of the FFT by q bins (and a constant phase that |.| drops).  The
+    // +-10 kHz / 500 Hz grid needs 2 forward FFTs per interval instead of 41, the 50-Hz grid 20 instead of 401.  The base
+    // of a class is its canonical member in [-500, 500) Hz -- whether or not that frequency is itself a bin -- so that a
+    // cell does not depend on which other bins are in the plan (bin-sharded searches stay bit-identical to unsharded ones)
+    // and the float32 phase arguments are as small as they can be.  GPSB200_ACQ_NOSHARE=1: every bin its own base.
+    std::vector<int32_t> bin_base(nbins), bin_shift(nbins);
+    std::vector<double> base_f;
+    const double df = (double)GR_FS / GR_N;
+    const bool share = getenv("GPSB200_ACQ_NOSHARE") == nullptr;
+    for (int b = 0; b < nbins; ++b) {
+        const double q = share ? floor(bin_hz[b] / df + 0.5) : 0.0;
+        const double f0 = bin_hz[b] - q * df;
+        if (fabs(q) >= GR_N / 2) { delete p; gr_set_error("gr_acq_plan_create: bin %d out of range", b); return GR_ERR_ARG; }
+        int found = -1;
+        for (size_t i = 0; share && i < base_f.size() && found < 0; ++i)
+            if (fabs(f0 - base_f[i]) < 1e-6) found = (int)i;
+        if (found < 0) { found = (int)base_f.size(); base_f.push_back(f0); }
+        bin_base[b] = found;
+        bin_shift[b] = (int32_t)((((long)q % GR_N) + GR_N) % GR_N);
+    }
+    p->nbase = (int)base_f.size();
+    std::vector<float> w(p->nbase);
+    for (int i = 0; i < p->nbase; ++i) w[i] = (float)(2.0 * 3.141592653589793 * base_f[i]);   // 2*np.pi*freq, then weak -> float32
     GR_CUDA(cudaSetDevice(gr_lib()->device));
     GR_CUDA(cudaMalloc(&p->d_prns, nprn * sizeof(int32_t)));
-    GR_CUDA(cudaMalloc(&p->d_w32, nbins * sizeof(float)));
+    GR_CUDA(cudaMalloc(&p->d_w32, p->nbase * sizeof(float)));
+    GR_CUDA(cudaMalloc(&p->d_bin_base, nbins * sizeof(int32_t)));
+    GR_CUDA(cudaMalloc(&p->d_bin_shift, nbins * sizeof(int32_t)));
     GR_CUDA(cudaMemcpy(p->d_prns, prns, nprn * sizeof(int32_t), cudaMemcpyHostToDevice));
-    GR_CUDA(cudaMemcpy(p->d_w32, w.data(), nbins * sizeof(float), cudaMemcpyHostToDevice));
+    GR_CUDA(cudaMemcpy(p->d_w32, w.data(), p->nbase * sizeof(float), cudaMemcpyHostToDevice));
+    GR_CUDA(cudaMemcpy(p->d_bin_base, bin_base.data(), nbins * sizeof(int32_t), cudaMemcpyHostToDevice));
+    GR_CUDA(cudaMemcpy(p->d_bin_shift, bin_shift.data(), nbins * sizeof(int32_t), cudaMemcpyHostToDevice));
     GR_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     *plan = p;
     return GR_OK;
@@ -661,6 +711,8 @@ extern "C" int gr_acq_plan_destroy(gr_acq_plan* p) {
     if (!p) return GR_OK;
     cudaFree(p->d_prns);
     cudaFree(p->d_w32);
+    cudaFree(p->d_bin_base);
+    cudaFree(p->d_bin_shift);
     if (p->d_in) cudaFree(p->d_in);
     if (p->d_out) cudaFree(p->d_out);
     if (p->d_cells) cudaFree(p->d_cells);
@@ -692,7 +744,7 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         gr_set_error("gr_acq_run_dev: rec_stride %lld shorter than one recording", (long long)rec_stride);
         return GR_ERR_ARG;
     }
-    const size_t spec_per_rec = (size_t)p->nbins * p->nnoncoh * GR_N * sizeof(float2);
+    const size_t spec_per_rec = (size_t)p->nbase * p->nnoncoh * 2 * GR_N * sizeof(float2);
     int sub = (int)(GR_ACQ_SPEC_CAP / spec_per_rec);
     if (sub < 1) sub = 1;
     if (sub > nrec) sub = nrec;
@@ -721,6 +773,9 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         a.rec_stride = rec_stride;
         a.prns = p->d_prns;
         a.w32 = p->d_w32;
+        a.bin_base = p->d_bin_base;
+        a.bin_shift = p->d_bin_shift;
+        a.nbase = p->nbase;
         a.nrec = nr;
         a.nprn = p->nprn;
         a.nbins = p->nbins;
@@ -735,10 +790,10 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         // forward grid: enough CTAs to fill the GPU a few times over, as many bins per CTA as that allows
         const long long units = (long long)nr * p->nnoncoh;
         long long nchunks = (4LL * gr_lib()->num_sms * 4 + units - 1) / units;
-        if (nchunks > p->nbins) nchunks = p->nbins;
+        if (nchunks > p->nbase) nchunks = p->nbase;
         if (nchunks < 1) nchunks = 1;
-        a.bins_per_chunk = (int)((p->nbins + nchunks - 1) / nchunks);
-        a.nchunks = (p->nbins + a.bins_per_chunk - 1) / a.bins_per_chunk;
+        a.bins_per_chunk = (int)((p->nbase + nchunks - 1) / nchunks);
+        a.nchunks = (p->nbase + a.bins_per_chunk - 1) / a.bins_per_chunk;
         const long long nfwd = units * a.nchunks;
         const long long ninv = (long long)nr * p->nbins * a.ngroups;
         if (nfwd > 0x7fffffffLL || ninv > 0x7fffffffLL) { gr_set_error("gr_acq_run_dev: grid too large"); return GR_ERR_ARG; }

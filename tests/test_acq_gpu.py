@@ -160,6 +160,34 @@ def test_weak_signal_fine_grid_vs_oracle(gpu, scen32):
     _check_cells(cells, ref)
 
 
+def test_shared_forward_spectra_equal_per_bin_spectra(gpu, monkeypatch):
+    """Bins 1 kHz apart share one forward spectrum (a circular shift of the FFT, gr_acq_plan_create); the per-bin form
+    (GPSB200_ACQ_NOSHARE, the reference's own float32 phase argument for every bin) gives the same cells within the
+    magnitude tolerance and the same arg-max wherever a peak is clear.  Bins that do not fit the 1-kHz lattice (odd
+    spacing) fall back to one spectrum each."""
+    from gps_sdr_receiver_b200 import synth
+    from gps_sdr_receiver_b200.acquisition import AcqPlan, GR_ACQ_POW
+    sats = [synth.Sat(prn=3, doppler=2440.0, delay=133.4, amp=0.1), synth.Sat(prn=17, doppler=-7010.0, delay=2001.7, amp=0.07),
+            synth.Sat(prn=30, doppler=9990.0, delay=0.2, amp=0.1)]
+    raw = synth.make_iq(sats, 10, seed=21)
+    prns = [1, 3, 17, 30]
+    for bins in ([-10000.0 + 500.0 * b for b in range(41)], [-3000.0 + 770.0 * b for b in range(9)]):
+        shared = AcqPlan(prns, bins, 1, 10, GR_ACQ_POW).run(raw)
+        monkeypatch.setenv("GPSB200_ACQ_NOSHARE", "1")
+        per_bin = AcqPlan(prns, bins, 1, 10, GR_ACQ_POW).run(raw)
+        monkeypatch.delenv("GPSB200_ACQ_NOSHARE")
+        for k in ("peak", "mean", "std", "z", "second"):
+            np.testing.assert_allclose(shared[k], per_bin[k], rtol=RTOL, err_msg=k)
+        clear = per_bin["z"] > 8.0
+        assert clear.sum() >= (3 if len(bins) == 41 else 0)
+        assert np.array_equal(shared["mx"][clear], per_bin["mx"][clear])
+    full = AcqPlan(prns, [-10000.0 + 500.0 * b for b in range(41)], 1, 10, GR_ACQ_POW).search(raw)
+    for s in sats:
+        b = full[0, prns.index(s.prn)]
+        assert abs(-10000.0 + 500.0 * int(b["bin"]) - s.doppler) <= 250.0
+        assert (int(b["cell"]["mx"]) - int(s.delay)) % 2048 in (0, 1)
+
+
 def test_ragged_and_invalid_inputs(gpu):
     from gps_sdr_receiver_b200 import _capi
     from gps_sdr_receiver_b200.acquisition import AcqPlan
