@@ -335,15 +335,17 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": R * REC_SAMPLES * 2,
                 "d2h_bytes_per_step": R * NPRN * ACQ_BEST.itemsize, "api": "AcqPlan.search -> gr_acq_search_host (C ABI), pinned host buffers"},
         "gpu_launches": launches,
-        "roofline": {"bound": "fp32", "kernel": "acq_inv_kernel (+ acq_fwd_kernel, 4 % of the launch pair)", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+        "roofline": {"bound": "fp32", "kernel": "acq_inv_kernel (+ acq_fwd_kernel, 0.5 % of the launch pair)", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp32_peak,
                      # dram__bytes_read + dram__bytes_write of the kernel pair, ncu --set full capture of 128 recordings
-                     # (profiles/acq_r01_v4_ncu_summary.md: 5.3 + 801.8 MB forward, 865.2 + 9.4 MB inverse), scaled to R
-                     "traffic": R * (5.3 + 801.8 + 865.2 + 9.4) * 1e6 / 128,
+                     # (profiles/acq_r01_v7_ncu_summary.md: 5.3 + 28.7 MB forward, 92.7 + 7.8 MB inverse), scaled to R
+                     "traffic": R * (5.3 + 28.7 + 92.7 + 7.8) * 1e6 / 128,
                      "peak_source": f"measured in this run: register-resident FFMA chains on all SMs (gr_debug_fp32_peak); "
                                     f"theoretical at 1965 MHz = {FP32_PEAK_THEORY:.1f}",
                      "flop_per_cell": FLOP_PER_CELL, "ms_per_launch": ms_kernel,
-                     "note": "BASELINE prescribes the FP32 FFT-flop roofline for acquisition; algorithmic flops = 5 N log2 N per FFT"},
+                     "note": "BASELINE prescribes the FP32 FFT-flop roofline for acquisition; algorithmic flops = 5 N log2 N per FFT of the "
+                             "reference's algorithm (one forward FFT per Doppler bin and interval: 4 % of the count); the kernels run 2 "
+                             "forward FFTs per interval and derive the other 39 bins as circular shifts"},
     }
 
     # ---------------- weak-signal fine acquisition (configs[3]): 10 ms x 20, 50 Hz bins, +-10 kHz ----------------
