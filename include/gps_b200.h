@@ -76,7 +76,11 @@ typedef struct gr_acq_plan gr_acq_plan;
  * Hz (float64, as the reference's python floats); tcoh_ms 1-ms blocks are summed
  * coherently (gpsrecv.py:250-254), nnoncoh such intervals are accumulated as |.|^2.
  * A recording must hold tcoh_ms*nnoncoh*2048 samples.  Wipe-off uses phase 0 and the
- * reference's float32 time base t[n] = (n+1)/fs (gpsrecv.py:32-33, 232-235). */
+ * reference's float32 time base t[n] = (n+1)/fs (gpsrecv.py:32-33, 232-235).
+ * Bins that differ by a multiple of fs/2048 = 1 kHz share one forward FFT (their spectra
+ * are circular shifts of each other); a cell's value does not depend on which other
+ * bins the plan holds.  |bin_hz| must stay below fs/2.  Environment (read at creation):
+ * GPSB200_ACQ_NOSHARE=1 one forward FFT per bin, as the reference computes it. */
 int gr_acq_plan_create(const int32_t* prns, int nprn, const double* bin_hz, int nbins,
                        int tcoh_ms, int nnoncoh, int mode, int in_format, gr_acq_plan** plan);
 int gr_acq_plan_destroy(gr_acq_plan* plan);
