@@ -18,6 +18,7 @@
 //                   the 2048 lags are reduced to one cell.  96 % of the time of a search.
 // acq_best_kernel then picks the best bin per (recording, PRN).
 #include <stdio.h>
+#include <string.h>
 #include <vector>
 
 #include "gr_fft2048t.cuh"      // includes gr_fft2048w.cuh and gr_fft2048.cuh
@@ -30,6 +31,7 @@ struct gr_acq_plan {
     float* d_w32;          // fl32(2*pi*f) per BASE bin (python-float product rounded once, gpsrecv.py:233)
     int32_t* d_bin_base;   // [nbins] base spectrum of a bin
     int32_t* d_bin_shift;  // [nbins] its circular shift in FFT bins, 0..2047
+    std::vector<int32_t> h_prns, h_bin_code;   // host copies: small plans travel in the kernel parameters (constant bank)
     // staging for the host entry point
     void* d_in;  size_t in_bytes;
     gr_acq_cell* d_out; size_t out_bytes;
@@ -40,6 +42,8 @@ struct gr_acq_plan {
     int last_launches;
 };
 
+#define GR_ACQ_MAX_PRN_C 64
+#define GR_ACQ_MAX_BIN_C 1024
 struct AcqArgs {
     const void* samples;
     long long rec_stride;      // samples
@@ -50,6 +54,11 @@ struct AcqArgs {
     int nrec, nprn, nbins, nbase, ngroups, tcoh, nnoncoh, mode;
     int nchunks, bins_per_chunk;   // forward kernel: base bins per CTA
     float scale;               // 1 / (tcoh * 2048)
+    // PRN list and (base << 16 | shift) per bin in the kernel parameters when they fit: the inverse kernel looks them up
+    // at job boundaries, where a global load would be an exposed L2 round trip (in_params = 0: use the arrays above)
+    int in_params;
+    int32_t prn_c[GR_ACQ_MAX_PRN_C];
+    int32_t bin_c[GR_ACQ_MAX_BIN_C];
     gr_acq_cell* out;
     float2* spec;              // scratch: forward spectra [nrec][nbase][nnoncoh][2][2048]: natural order, and shifted by one bin
     GrTables tab;
@@ -426,11 +435,13 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
     // The spectrum of (recording, bin, interval k) is the base spectrum of the bin's 1-kHz class rotated by the bin's
     // shift: copy (shift & 1) of the pair the forward kernel wrote, rotated by the even part (tma_load_rot).
     constexpr size_t kStrideK = 2 * (size_t)GR_N * 8;                            // bytes between intervals
+    auto prn_of = [&](int i) -> int { return a.in_params ? a.prn_c[i] : a.prns[i]; };
     auto item_src = [&](int wk, int& rot_out) -> const char* {
         const int b = (wk / a.ngroups) % a.nbins, r = wk / (a.ngroups * a.nbins);
-        const int sh = a.bin_shift[b];
+        const int code = a.in_params ? a.bin_c[b] : ((a.bin_base[b] << 16) | a.bin_shift[b]);
+        const int sh = code & 0xffff;
         rot_out = sh & ~1;
-        return reinterpret_cast<const char*>(a.spec) + ((size_t)(r * a.nbase + a.bin_base[b]) * a.nnoncoh * 2 + (sh & 1)) * (GR_N * 8);
+        return reinterpret_cast<const char*>(a.spec) + ((size_t)(r * a.nbase + (code >> 16)) * a.nnoncoh * 2 + (sh & 1)) * (GR_N * 8);
     };
     int rot;
     const char* spec = item_src(work, rot);
@@ -466,7 +477,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
         }
         tm_st16(tm + kColTw2, w);
         tm_st16(tm + kColTw2 + 16, w + 16);
-        load_conjspec<true>(w, a.tab.conjspec + (size_t)a.prns[grp * G] * GR_N + t);
+        load_conjspec<true>(w, a.tab.conjspec + (size_t)prn_of(grp * G) * GR_N + t);
         tm_st16(tm + kColC, w);
         tm_st16(tm + kColC + 16, w + 16);
         tm_wait_st();
@@ -486,7 +497,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             if (!(TM & 2)) tw2[(TM & 2) ? 0 : i] = cf{u.x, u.y};
         }
         if (TM & 2) { tm_st16(tm + kColTw2, w); tm_st16(tm + kColTw2 + 16, w + 16); }
-        load_conjspec<false>(w, a.tab.conjspec + (size_t)a.prns[grp * G] * GR_N + t);     // first job's conjugate code spectrum
+        load_conjspec<false>(w, a.tab.conjspec + (size_t)prn_of(grp * G) * GR_N + t);     // first job's conjugate code spectrum
         tm_st16(tm + kColC, w);
         tm_st16(tm + kColC + 16, w + 16);
         tm_wait_st();
@@ -630,7 +641,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
         const bool has_next = n_work < nwork;
         const int n_grp = n_work % a.ngroups;
         float w[32];
-        if (has_next) load_conjspec<PK>(w, a.tab.conjspec + (size_t)a.prns[n_grp * G + n_g] * GR_N + t);
+        if (has_next) load_conjspec<PK>(w, a.tab.conjspec + (size_t)prn_of(n_grp * G + n_g) * GR_N + t);
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] *= sc;
         acq_cell_epilogue(acc, obase, t, a.out + ((size_t)rec * a.nprn + grp * G + g) * a.nbins + bin, &scratch);
@@ -691,6 +702,9 @@ extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* b
         bin_shift[b] = (int32_t)((((long)q % GR_N) + GR_N) % GR_N);
     }
     p->nbase = (int)base_f.size();
+    p->h_prns.assign(prns, prns + nprn);
+    p->h_bin_code.resize(nbins);
+    for (int b = 0; b < nbins; ++b) p->h_bin_code[b] = (bin_base[b] << 16) | bin_shift[b];
     std::vector<float> w(p->nbase);
     for (int i = 0; i < p->nbase; ++i) w[i] = (float)(2.0 * 3.141592653589793 * base_f[i]);   // 2*np.pi*freq, then weak -> float32
     GR_CUDA(cudaSetDevice(gr_lib()->device));
@@ -773,6 +787,11 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         a.rec_stride = rec_stride;
         a.prns = p->d_prns;
         a.w32 = p->d_w32;
+        a.in_params = (p->nprn <= GR_ACQ_MAX_PRN_C && p->nbins <= GR_ACQ_MAX_BIN_C && p->nbase < 32768) ? 1 : 0;
+        if (a.in_params) {
+            memcpy(a.prn_c, p->h_prns.data(), p->nprn * sizeof(int32_t));
+            memcpy(a.bin_c, p->h_bin_code.data(), p->nbins * sizeof(int32_t));
+        }
         a.bin_base = p->d_bin_base;
         a.bin_shift = p->d_bin_shift;
         a.nbase = p->nbase;
