@@ -12,7 +12,10 @@ Workload at every N (weak scaling): BASELINE.json configs[1] "cold-start acquisi
 non-coherent, synthetic uint8 I/Q at 2.048 MS/s.  One grid is only 2.7 Mcells / 1.8 GFLOP, so a
 "step" searches a batch of `--recs` independent 10-ms recordings per GPU in one launch.
 The `tracking` object of the same line is configs[2]: 12 channels, 8-ms epochs, a 10-minute
-synthetic recording per GPU.  See DESIGN.md "Measurement".
+synthetic recording per GPU; `acq_fine` is configs[3] (10 ms x 20, 401 bins) with every rank searching
+its own recordings and, for N > 1, `acq_fine_sharded` the same search for ONE set of recordings with
+its Doppler bins sharded across the ranks; `tracking_batch` the per-GPU share of configs[4].
+See DESIGN.md "Measurement".
 """
 from __future__ import annotations
 
