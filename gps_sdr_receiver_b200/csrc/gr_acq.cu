@@ -398,6 +398,21 @@ __device__ __forceinline__ void load_conjspec(float* w, const float2* cs) {
     }
 }
 
+// ... the same from this thread's private slots of a shared-memory copy (slot j = 8 bytes at (t + 128 j) * 8)
+template <bool PK>
+__device__ __forceinline__ void conjspec_from_smem(float* w, const float2* slots) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float2 v = slots[128 * j];
+        if constexpr (PK) {
+            const int j0 = j & 3, m = j >> 2, q = 16 * (j0 >> 1) + 2 * (4 * (j0 & 1) + m);
+            w[q] = v.y; w[q + 1] = v.x;
+        } else {
+            w[2 * j] = v.x; w[2 * j + 1] = v.y;
+        }
+    }
+}
+
 // FFT: gr_fft2048t.cuh (exchange 1 in shared memory with 128-bit stores on a double-buffered 16 KiB buffer and
 // ONE block barrier per transform; exchange 2 + radix-8 through TMEM).  TM bit 1 / bit 2: stage-2 / stage-1
 // twiddles in TMEM (else registers).
@@ -510,9 +525,13 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
 
     while (true) {
         // first spectrum of the job after this one (same bin or next work item); fetched during this job's last transform
+        int n_work = work, n_g = g + 1;
+        if (n_g >= G || grp * G + n_g >= a.nprn) { n_g = 0; n_work = work + gridDim.x; }
+        const bool has_next = n_work < nwork;
+        const int n_grp = n_work % a.ngroups;
         const char* xjob_next = spec;
         int rot_next = rot;
-        if (g + 1 >= G || grp * G + g + 1 >= a.nprn) xjob_next = work + (int)gridDim.x < nwork ? item_src(work + gridDim.x, rot_next) : nullptr;
+        if (n_work != work) xjob_next = has_next ? item_src(n_work, rot_next) : nullptr;
         float acc[16];                                          // non-coherent accumulators, 16 lags per thread
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = 0.f;
@@ -549,6 +568,16 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             float wa[16], wb[16];
             tm_ld16_issue(tm + kColTw1, wa);                     // arrives while the block waits at the barrier
             __syncthreads();
+            if (k + 1 == a.nnoncoh && has_next) {
+                // next PRN's conjugate code spectrum: global -> this thread's private slots of the exchange buffer that stays
+                // free until the next job's first transform (cp.async: no registers, no wait; same L1 traffic as a load)
+                const float2* cs = a.tab.conjspec + (size_t)prn_of(n_grp * G + n_g) * GR_N + t;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_raw + par * GR_W_BUF1_BYTES) + t * 8;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 1024 * j), "l"(cs + 128 * j) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
             {                                                    // every thread has consumed X_k: refill the stage
                 const bool more = k + 1 < a.nnoncoh;
                 const char* src = more ? spec + (size_t)(k + 1) * kStrideK : xjob_next;
@@ -608,6 +637,16 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             fftw_ex1_write(b1, t, y);
             if (TM & 2) tm_ld16_issue(tm + kColTw2, wa);         // arrives while the block waits at the barrier
             __syncthreads();
+            if (k + 1 == a.nnoncoh && has_next) {
+                // next PRN's conjugate code spectrum: global -> this thread's private slots of the exchange buffer that stays
+                // free until the next job's first transform (cp.async: no registers, no wait; same L1 traffic as a load)
+                const float2* cs = a.tab.conjspec + (size_t)prn_of(n_grp * G + n_g) * GR_N + t;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_raw + par * GR_W_BUF1_BYTES) + t * 8;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 1024 * j), "l"(cs + 128 * j) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
             {                                                    // every thread has consumed X_k: refill the stage
                 const bool more = k + 1 < a.nnoncoh;
                 const char* src = more ? spec + (size_t)(k + 1) * kStrideK : xjob_next;
@@ -635,19 +674,20 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
             }
           }
         }
-        // the job after this one; its conjugate spectrum is loaded now: L2 latency hidden behind the cell reduction
-        int n_work = work, n_g = g + 1;
-        if (n_g >= G || grp * G + n_g >= a.nprn) { n_g = 0; n_work = work + gridDim.x; }
-        const bool has_next = n_work < nwork;
-        const int n_grp = n_work % a.ngroups;
-        float w[32];
-        if (has_next) load_conjspec<PK>(w, a.tab.conjspec + (size_t)prn_of(n_grp * G + n_g) * GR_N + t);
+        if (has_next) {
+            // park the next job's code spectrum (this warp is done with the current one); the copy was started half a
+            // transform ago, and the cell reduction's barriers keep the buffer from being overwritten before every
+            // thread has read its slots
+            float w[32];
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            conjspec_from_smem<PK>(w, reinterpret_cast<const float2*>(smem_raw + par * GR_W_BUF1_BYTES) + t);
+            tm_st16(tm + kColC, w);
+            tm_st16(tm + kColC + 16, w + 16);
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] *= sc;
         acq_cell_epilogue(acc, obase, t, a.out + ((size_t)rec * a.nprn + grp * G + g) * a.nbins + bin, &scratch);
         if (!has_next) break;
-        tm_st16(tm + kColC, w);
-        tm_st16(tm + kColC + 16, w + 16);
         tm_wait_st();
         if (n_work != work) {
             work = n_work; grp = n_grp; bin = (work / a.ngroups) % a.nbins; rec = work / (a.ngroups * a.nbins);
