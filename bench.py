@@ -562,7 +562,7 @@ def run_b200(args):
                 "metric": "tracking x-realtime, aggregate over independent recordings", "value": world * RB * secs / t_batch,
                 "unit": "x-realtime", "seconds": t_batch,
                 "config": {"workload": f"{RB} recordings x {TRACK_NCH} channels per GPU, {secs:.0f} s each, 8-ms epochs, one launch "
-                                       f"({RB * TRACK_NCH} channel CTAs; per-GPU share of BASELINE configs[4])"},
+                                       f"({RB * TRACK_NCH} channel CTAs, all resident: 3 per SM in the kernel's dense form; per-GPU share of BASELINE configs[4])"},
                 "roofline": {"bound": "hbm", "kernel": "track_kernel", "achieved": (b_raw + b_out) / t_batch / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": (b_raw + b_out) / t_batch / 1e9 / hbm_peak, "traffic": None,
                              "fp32_achieved_tflops": nb_ep * RB * TRACK_NCH * flop_ce / t_batch / 1e12, "fp32_peak_tflops": fp32_peak,
@@ -597,7 +597,7 @@ def main():
     ap.add_argument("--recs", type=int, default=512, help="independent 10-ms recordings per GPU per step")
     ap.add_argument("--track-seconds", type=float, default=600.0)
     ap.add_argument("--track-reps", type=int, default=2)
-    ap.add_argument("--batch-recs", type=int, default=24, help="recordings per GPU in the batched tracking line (0 = skip)")
+    ap.add_argument("--batch-recs", type=int, default=32, help="recordings per GPU in the batched tracking line (0 = skip); 32 = 256 / 8, BASELINE configs[4]")
     ap.add_argument("--batch-seconds", type=float, default=60.0)
     ap.add_argument("--fine-recs", type=int, default=16, help="recordings per GPU in the weak-signal fine-acquisition line")
     ap.add_argument("--skip-fine", action="store_true")

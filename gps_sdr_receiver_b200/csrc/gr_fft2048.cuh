@@ -150,17 +150,24 @@ GR_HD void fft_ex2_read_stage3(const cf* buf2, int t, cf* v) {
 // Forward FFT-2048 across the 128 threads of a CTA (or of a 128-thread group
 // using its own buffers and `bar_id` as named barrier).  smem = buf1 | buf2.
 // TW1_STRIDE > 1: stage-1 twiddles read from a shared-memory table laid out [k][thread].
-template <bool kWholeCta, int TW1_STRIDE = 1>
+// kOneBuf: both transposes go through ONE buffer of GR_ONEBUF_BYTES (two more barriers per transform: before the first
+// store, because the previous transform's last loads read the same memory, and between the first transpose's loads and
+// the second one's stores).  Same arithmetic, same results; for callers that are short of shared memory.
+#define GR_ONEBUF_BYTES (GR_B1_ELEMS * 8)              // 17408 >= GR_B2_ELEMS * 8
+template <bool kWholeCta, int TW1_STRIDE = 1, bool kOneBuf = false>
 __device__ __forceinline__ void fft2048(cf* v, cf* smem, const cf* tw1, const cf* tw2, int t, int bar_id = 1) {
     cf* buf1 = smem;
-    cf* buf2 = smem + GR_B1_ELEMS;
+    cf* buf2 = kOneBuf ? smem : smem + GR_B1_ELEMS;
+    auto sync = [&]() { if (kWholeCta) __syncthreads(); else asm volatile("bar.sync %0, 128;" ::"r"(bar_id)); };
     fft_stage1<TW1_STRIDE>(v, tw1);
+    if (kOneBuf) sync();
     fft_ex1_write(buf1, t, v);
-    if (kWholeCta) __syncthreads(); else asm volatile("bar.sync %0, 128;" ::"r"(bar_id));
+    sync();
     fft_ex1_read(buf1, t, v);
     fft_stage2(v, tw2);
+    if (kOneBuf) sync();
     fft_ex2_write(buf2, t, v);
-    if (kWholeCta) __syncthreads(); else asm volatile("bar.sync %0, 128;" ::"r"(bar_id));
+    sync();
     fft_ex2_read_stage3(buf2, t, v);
 }
 #endif

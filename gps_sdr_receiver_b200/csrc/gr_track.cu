@@ -90,6 +90,8 @@ struct TrackArgs {
     int n_epochs, n_active;
     int out_tma;            // records leave by cp.async.bulk (16-byte aligned output array)
     int stage;              // raw I/Q of each epoch staged in shared memory by TMA (u8 input, 16-byte aligned recordings)
+    int buf_bytes;          // size of the scratch buffer in front of TrackSmem (FFT buffers / staged prompt rows)
+    int part_rows;          // prompt rows staged per reduction round
     const int32_t* slots;
     GrChan* state;
     gr_epoch_out* out;
@@ -98,8 +100,11 @@ struct TrackArgs {
 };
 
 // ---- shared-memory scratch -------------------------------------------------------------------
-#define GR_PART_ROWS 17                                   // prompt passes staged per reduction round
+#define GR_PART_ROWS 17                                   // prompt passes staged per reduction round (at most)
 #define GR_TRACK_BUF_BYTES (GR_PART_ROWS * 128 * 16)      // 34816 >= GR_FFT_SMEM_BYTES; FFT buffers alias it
+// The "dense" form of the kernel (batches: more channels than 2 x SMs) fits THREE CTAs per SM at 8-ms epochs: the FFT
+// runs in its one-buffer mode and the prompt rows are staged n_cyc + 1 at a time, so the scratch buffer shrinks from
+// 34 KB to 18 KB (71 KB per CTA with the 32 KB raw stage), and the register cap drops from 190 to 168.
 
 struct TrackSmem {
     gr_epoch_out out[2];                 // the epoch's record is assembled here (448 B each, 16-byte aligned) and leaves by TMA
@@ -175,9 +180,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- correlation: folded samples F (natural FFT layout) -> statistics of |ifft(fft(F)/avg * conjC)| --
 // Leaves mx in S->sh_i[4], z / mean / std / corr[mx-1..mx+1] in S; ends with a barrier.
+template <bool kOneBuf>
 __device__ __forceinline__ void corr_and_stats(cf* F, const float2* __restrict__ cs, float scale, cf* fftbuf,
                                                const cf* tw1, const cf* tw2, int t, TrackSmem* S) {
-    fft2048<true>(F, fftbuf, tw1, tw2, t);
+    fft2048<true, 1, kOneBuf>(F, fftbuf, tw1, tw2, t);
     cf y[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -185,7 +191,7 @@ __device__ __forceinline__ void corr_and_stats(cf* F, const float2* __restrict__
         y[j].x = F[j].x * c.y + F[j].y * c.x;      // swap form of the inverse transform
         y[j].y = F[j].x * c.x - F[j].y * c.y;
     }
-    fft2048<true>(y, fftbuf, tw1, tw2, t);
+    fft2048<true, 1, kOneBuf>(y, fftbuf, tw1, tw2, t);
     float st[16];
     float s = 0.f, s2 = 0.f, mx = -1.f;
     int idx = 0;
@@ -372,13 +378,13 @@ __device__ __forceinline__ void trk_stage_issue(void* dst, const char* gsrc, uns
 // the previous epoch's serial tail (prompt means, edge detector, PLL) runs; both sample passes then read
 // shared memory instead of L2/HBM -- a single recording is a chain of dependent epochs, so load latency,
 // not bandwidth, is what the epoch time is made of.
-template <int IN_FMT, bool kStage>
-__global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a) {
+template <int IN_FMT, bool kStage, bool kDense = false>
+__global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(const TrackArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* fftbuf = reinterpret_cast<cf*>(smem_raw);
     float4* part = reinterpret_cast<float4*>(smem_raw);          // aliases the FFT buffers
-    TrackSmem* S = reinterpret_cast<TrackSmem*>(smem_raw + GR_TRACK_BUF_BYTES);
-    unsigned char* stage = smem_raw + GR_TRACK_BUF_BYTES + ((sizeof(TrackSmem) + 15) & ~(size_t)15);
+    TrackSmem* S = reinterpret_cast<TrackSmem*>(smem_raw + a.buf_bytes);
+    unsigned char* stage = smem_raw + a.buf_bytes + ((sizeof(TrackSmem) + 15) & ~(size_t)15);
     GrChanHot* C = &S->CH.h;
 
     const int t = threadIdx.x;
@@ -464,7 +470,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
                 __syncthreads();
                 cf F[16];
                 fold_blocks<IN_FMT, kStage>(F, src, 0, avg, rt, t, S);
-                corr_and_stats(F, cs, 1.0f / ((float)avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
+                corr_and_stats<kDense>(F, cs, 1.0f / ((float)avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
                 z = S->z;
                 if (z > (double)a.cfg.corr_min) {
                     delay = S->sh_i[4];
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
             {
                 cf F[16];
                 fold_blocks<IN_FMT, kStage>(F, src, (n_cyc - corr_avg) / 2, corr_avg, rt, t, S);
-                corr_and_stats(F, cs, 1.0f / ((float)corr_avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
+                corr_and_stats<kDense>(F, cs, 1.0f / ((float)corr_avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
             }
             if (t == 0) {
                 int delay = -1;
@@ -556,8 +562,8 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
                     if ((t & 31) == 0) S->qred[t >> 5][m] = v[m];
                 }
             }
-            for (int k0 = 0; k0 <= n_cyc; k0 += GR_PART_ROWS) {
-                const int k1 = (k0 + GR_PART_ROWS <= n_cyc + 1) ? k0 + GR_PART_ROWS : n_cyc + 1;
+            for (int k0 = 0; k0 <= n_cyc; k0 += a.part_rows) {
+                const int k1 = (k0 + a.part_rows <= n_cyc + 1) ? k0 + a.part_rows : n_cyc + 1;
                 for (int k = k0; k < k1; ++k) {
                     const long long base = (long long)128 * jb + (long long)GR_N * (k - 1) + t;
                     // rows outside the epoch (pass 0: not yet wrapped, last pass: wrapped) read a clamped
@@ -865,7 +871,13 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) track_kernel(const TrackArgs a
 }
 
 // ---- host API ------------------------------------------------------------------------------------------
-static size_t track_smem_bytes() { return GR_TRACK_BUF_BYTES + ((sizeof(TrackSmem) + 15) & ~(size_t)15); }
+static size_t track_smem_bytes(size_t buf_bytes = GR_TRACK_BUF_BYTES) { return buf_bytes + ((sizeof(TrackSmem) + 15) & ~(size_t)15); }
+// dense form: one-buffer FFT, prompt rows staged min(n_cyc + 1, GR_PART_ROWS) at a time
+static int track_dense_rows(int n_cyc) { return n_cyc + 1 < GR_PART_ROWS ? n_cyc + 1 : GR_PART_ROWS; }
+static size_t track_dense_buf_bytes(int n_cyc) {
+    const size_t rows = (size_t)track_dense_rows(n_cyc) * 128 * 16;
+    return rows > GR_ONEBUF_BYTES ? rows : (size_t)GR_ONEBUF_BYTES;
+}
 static size_t track_stage_bytes(int n_cyc) { return (size_t)n_cyc * GR_N * 2; }
 
 extern "C" int gr_track_default_cfg(gr_track_cfg* cfg) {
@@ -907,6 +919,8 @@ extern "C" int gr_track_bank_create(const gr_track_cfg* cfg, gr_track_bank** ban
     GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)track_smem_bytes()));
     GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_CF32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)track_smem_bytes()));
     GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(track_smem_bytes() + track_stage_bytes(GR_MAX_NCYC))));
+    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(track_smem_bytes() + track_stage_bytes(GR_MAX_NCYC))));
     *bank = b;
     return GR_OK;
@@ -1030,7 +1044,18 @@ extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int
     // TMA needs 16-byte aligned sources: every recording's first sample, hence base and stride
     a.out_tma = ((uintptr_t)d_out % 16) == 0;
     a.stage = b->cfg.in_format == GR_IN_U8IQ && ((uintptr_t)d_samples % 16) == 0 && ((2 * rec_stride) % 16) == 0;
-    if (a.stage)
+    a.buf_bytes = GR_TRACK_BUF_BYTES;
+    a.part_rows = GR_PART_ROWS;
+    // dense form when the launch has more channels than fit at two CTAs per SM and the epoch is short enough for three
+    const char* dense_env = getenv("GPSB200_TRACK_DENSE");          // development / test switch: 0 = never, 1 = whenever it fits
+    const size_t dense_smem = track_smem_bytes(track_dense_buf_bytes(b->cfg.n_cyc)) + track_stage_bytes(b->cfg.n_cyc);
+    const bool dense = a.stage && 3 * (dense_smem + 1024) <= 227 * 1024 &&
+                       (dense_env ? atoi(dense_env) != 0 : a.n_active > 2 * gr_lib()->num_sms);
+    if (dense) {
+        a.buf_bytes = (int)track_dense_buf_bytes(b->cfg.n_cyc);
+        a.part_rows = track_dense_rows(b->cfg.n_cyc);
+        track_kernel<GR_IN_U8IQ, true, true><<<a.n_active, GR_FFT_THREADS, dense_smem, s>>>(a);
+    } else if (a.stage)
         track_kernel<GR_IN_U8IQ, true><<<a.n_active, GR_FFT_THREADS, track_smem_bytes() + track_stage_bytes(b->cfg.n_cyc), s>>>(a);
     else if (b->cfg.in_format == GR_IN_U8IQ)
         track_kernel<GR_IN_U8IQ, false><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);

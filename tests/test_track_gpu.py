@@ -246,3 +246,29 @@ def test_ncyc16_with_stream_gap_and_sweep_request_matches_oracle(gpu):
                 assert abs(r["max_corr"] - ch.max_corr) <= 1e-4 * abs(ch.max_corr) + 1e-6, tag
     assert all(ch.locked for ch in chans)
     bank.close()
+
+
+def test_dense_form_equals_standard_form_bit_for_bit(gpu, monkeypatch):
+    """The three-CTAs-per-SM form of the tracking kernel (one-buffer FFT, prompt rows staged n_cyc + 1 at a time; chosen
+    by the launcher for batches of more than 2 x SMs channels) does the same arithmetic in the same order: its records
+    are bit-identical to the standard form's, here on a small bank with the form forced by GPSB200_TRACK_DENSE."""
+    import torch
+    from gps_sdr_receiver_b200 import synth
+    from gps_sdr_receiver_b200.tracking import TrackBank
+    n_cyc, ngps, n_ep = 8, 8 * 2048, 300
+    sats = [synth.Sat(prn=4, doppler=1210.0, delay=100.3, amp=0.08, bit_offset_ms=3, bit_seed=5),
+            synth.Sat(prn=19, doppler=-3390.0, delay=1999.7, amp=0.08, bit_offset_ms=11, bit_seed=6),
+            synth.Sat(prn=31, doppler=40.0, delay=1023.5, amp=0.06, bit_offset_ms=0, bit_seed=7)]
+    raw = torch.from_numpy(synth.make_iq(sats, n_ep * n_cyc, seed=5)).cuda()
+    out = {}
+    for dense in ("0", "1"):
+        monkeypatch.setenv("GPSB200_TRACK_DENSE", dense)
+        bank = TrackBank(n_cyc, 4)
+        for s in sats:
+            bank.add(s.prn, 50.0 * round(s.doppler / 50.0), (int(s.delay) + 1) % 2048)
+        out[dense] = TrackBank.records_from_tensor(bank.process_dev(raw, ngps, n_ep)).copy()
+        torch.cuda.synchronize()
+        bank.close()
+    monkeypatch.delenv("GPSB200_TRACK_DENSE")
+    assert out["0"].tobytes() == out["1"].tobytes()
+    assert out["1"]["locked"][-1].all()
