@@ -9,13 +9,15 @@
 // and the generalisation BASELINE.json names (tcoh coherent x nnoncoh non-coherent).
 //
 // Two grid kernels:
-//   acq_fwd_kernel  CTA = (recording, non-coherent interval, chunk of Doppler bins): wipe-off, fold of the tcoh
-//                   1-ms blocks in the time domain (sum of FFTs = FFT of the sum), ONE forward FFT per bin; the
-//                   spectra go to a scratch array (L2 / HBM) in the layout the inverse kernel's TMA stage reads.
+//   acq_fwd_kernel  CTA = (recording, non-coherent interval, chunk of BASE bins): wipe-off, fold of the tcoh
+//                   1-ms blocks in the time domain (sum of FFTs = FFT of the sum), ONE forward FFT per base bin.  Doppler
+//                   bins 1 kHz (= fs / 2048) apart have spectra that are circular shifts of each other, so only one
+//                   spectrum per 1-kHz class is computed (gr_acq_plan_create); it goes to a scratch array (L2) in natural
+//                   order, twice (plain and shifted by one bin: any rotation becomes 16-byte aligned bulk copies).
 //   acq_inv_kernel  persistent, 4 CTAs / SM; work item = (recording, Doppler bin, group of 4 PRNs).  Per PRN and
-//                   interval: spectrum by TMA into shared memory, x conj code spectrum (held in tensor memory),
-//                   FFT-2048 with its second transpose through tensor memory, |.|^2 accumulated on chip; per PRN
-//                   the 2048 lags are reduced to one cell.  96 % of the time of a search.
+//                   interval: the bin's rotated spectrum by TMA into shared memory, x conj code spectrum (held in tensor
+//                   memory), FFT-2048 on the packed FP32 instructions with its second transpose through tensor memory,
+//                   |.|^2 accumulated on chip; per PRN the 2048 lags are reduced to one cell.  99 % of the time of a search.
 // acq_best_kernel then picks the best bin per (recording, PRN).
 #include <stdio.h>
 #include <string.h>
@@ -90,10 +92,10 @@ __device__ __forceinline__ float nco_arg(float w32, long long n) {
 }
 
 // ---- kernel 1: forward spectra ------------------------------------------------------------------
-// CTA = (recording, non-coherent interval, chunk of Doppler bins); it loops over its bins with the FFT
+// CTA = (recording, non-coherent interval, chunk of base bins); it loops over its bins with the FFT
 // twiddles (and, for tcoh = 1, the 16 samples per thread) held in registers: wipe-off, time-domain fold of
-// the tcoh blocks, ONE forward FFT per bin; the spectrum goes to the plan's scratch in the paired layout
-// [j >> 1][t][j & 1] the inverse kernel's TMA stage expects (8 x 128-bit per thread).
+// the tcoh blocks, ONE forward FFT per base bin; the spectrum goes to the plan's scratch in natural order, twice
+// (E0[m] = X[m], E1[m] = X[m + 1]), which is what the inverse kernel's rotated TMA fetch expects.
 //
 // NCO: the phase argument is the reference's float32 one, arg = fl32(w32 * fl32((n+1)/fs))
 // (gpsrecv.py:32-33, 232-235); sin/cos of it come from a 2-constant Cody-Waite reduction + MUFU
