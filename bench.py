@@ -34,6 +34,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "acq cells/s (PRN x Doppler x code-phase)"
+WORKLOAD = ("cold-start acquisition 32 PRN x 41 Doppler (+-10 kHz, 500 Hz) x 2048 code phases, 1 ms coherent x 10 "
+            "non-coherent, uint8 IQ 2.048 MS/s (BASELINE configs[1])")
 NPRN, NBIN, NLAG, TCOH, NNONCOH = 32, 41, 2048, 1, 10
 BINS = [-10000.0 + 500.0 * b for b in range(NBIN)]
 PRNS = list(range(1, NPRN + 1))
@@ -200,7 +202,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64/c64 (numpy)", "data": "synthetic",
-            "config": {"workload": "cold-start acquisition 32 PRN x 41 Doppler x 2048 code phases, 1 ms x 10 non-coherent, uint8 IQ",
+            "config": {"workload": WORKLOAD,
                        "recordings_per_step": workers},
             "cpu_baseline": {"value": value, "unit": "cells/s", "cores": workers, "kind": "port",
                              "sample": f"{workers} full grids per step, one per worker process (multiprocessing spawn pool)"},
@@ -330,8 +332,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "cold-start acquisition 32 PRN x 41 Doppler (+-10 kHz, 500 Hz) x 2048 code phases, 1 ms coherent x 10 "
-                               "non-coherent, uint8 IQ 2.048 MS/s (BASELINE configs[1])",
+        "config": {"workload": WORKLOAD,
                    "recordings_per_gpu_per_step": R, "cells_per_recording": CELLS_PER_REC,
                    "l2": f"inputs rotate over {NBUF} batches = {NBUF * R * REC_SAMPLES * 2 / 2**20:.0f} MiB > 126 MiB L2",
                    "multi_gpu": "recordings partitioned across ranks; NCCL all_gather of the per-GPU peak tuples each step"},
