@@ -26,6 +26,7 @@
 #include "gr_fft2048t.cuh"      // includes gr_fft2048w.cuh and gr_fft2048.cuh
 #include "gr_internal.h"
 
+#define GR_ACQ_HOST_CHUNKS 4
 struct gr_acq_plan {
     int nprn, nbins, tcoh, nnoncoh, mode, in_format;
     int nbase;             // distinct forward spectra per (recording, interval): bins 1 kHz apart share one, see gr_acq_plan_create
@@ -41,6 +42,9 @@ struct gr_acq_plan {
     gr_acq_best* d_best; size_t best_bytes;
     float2* d_spec; size_t spec_bytes;            // forward spectra of one sub-batch of recordings
     cudaStream_t stream;
+    cudaStream_t s_in;                            // host entry points: copy-in stream and per-chunk events (created on first use)
+    cudaEvent_t ev_in[GR_ACQ_HOST_CHUNKS];
+    bool pipe_ready;
     int last_launches;
 };
 
@@ -721,6 +725,7 @@ extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* b
     p->d_in = nullptr; p->in_bytes = 0; p->d_out = nullptr; p->out_bytes = 0; p->last_launches = 0;
     p->d_cells = nullptr; p->cells_bytes = 0; p->d_best = nullptr; p->best_bytes = 0;
     p->d_spec = nullptr; p->spec_bytes = 0;
+    p->pipe_ready = false;
     // Bins whose frequencies differ by a multiple of fs / 2048 = 1 kHz share ONE forward spectrum: the wipe-off factor
     // exp(-i 2 pi q 1000 (n + 1) / fs) = exp(-i 2 pi q (n + 1) / 2048) is the same in every 1-ms block, so it commutes with
     // the coherent fold and turns into a circular shift of the FFT by q bins (and a constant phase that |.| drops).  The
@@ -774,6 +779,10 @@ extern "C" int gr_acq_plan_destroy(gr_acq_plan* p) {
     if (p->d_cells) cudaFree(p->d_cells);
     if (p->d_best) cudaFree(p->d_best);
     if (p->d_spec) cudaFree(p->d_spec);
+    if (p->pipe_ready) {
+        cudaStreamDestroy(p->s_in);
+        for (int i = 0; i < GR_ACQ_HOST_CHUNKS; ++i) cudaEventDestroy(p->ev_in[i]);
+    }
     cudaStreamDestroy(p->stream);
     delete p;
     return GR_OK;
@@ -946,9 +955,34 @@ extern "C" int gr_acq_search_host(gr_acq_plan* p, const void* h_samples, int nre
     if (rc != GR_OK) return rc;
     rc = grow((void**)&p->d_best, &p->best_bytes, best_bytes);
     if (rc != GR_OK) return rc;
-    GR_CUDA(cudaMemcpyAsync(p->d_in, h_samples, in_bytes, cudaMemcpyHostToDevice, p->stream));
-    rc = gr_acq_search_dev(p, p->d_in, nrec, rec_stride, p->d_best, (void*)p->stream);
-    if (rc != GR_OK) return rc;
+    if (nrec < 2 * GR_ACQ_HOST_CHUNKS) {
+        GR_CUDA(cudaMemcpyAsync(p->d_in, h_samples, in_bytes, cudaMemcpyHostToDevice, p->stream));
+        rc = gr_acq_search_dev(p, p->d_in, nrec, rec_stride, p->d_best, (void*)p->stream);
+        if (rc != GR_OK) return rc;
+    } else {
+        // batches: the recordings go in as GR_ACQ_HOST_CHUNKS pieces on a copy stream, each searched as soon as it has
+        // arrived, so that only the first piece's host-to-device copy is not hidden behind the kernels
+        if (!p->pipe_ready) {
+            GR_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+            for (int i = 0; i < GR_ACQ_HOST_CHUNKS; ++i) GR_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+            p->pipe_ready = true;
+        }
+        const int per = (nrec + GR_ACQ_HOST_CHUNKS - 1) / GR_ACQ_HOST_CHUNKS;
+        int launches = 0;
+        for (int c = 0, r0 = 0; r0 < nrec; ++c, r0 += per) {
+            const int nr = r0 + per <= nrec ? per : nrec - r0;
+            const size_t off = (size_t)r0 * (size_t)rec_stride * bps;
+            const size_t len = ((size_t)(nr - 1) * (size_t)rec_stride + rec_len) * bps;
+            GR_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(p->d_in) + off, reinterpret_cast<const char*>(h_samples) + off, len,
+                                    cudaMemcpyHostToDevice, p->s_in));
+            GR_CUDA(cudaEventRecord(p->ev_in[c], p->s_in));
+            GR_CUDA(cudaStreamWaitEvent(p->stream, p->ev_in[c], 0));
+            rc = gr_acq_search_dev(p, reinterpret_cast<char*>(p->d_in) + off, nr, rec_stride, p->d_best + (size_t)r0 * p->nprn, (void*)p->stream);
+            if (rc != GR_OK) return rc;
+            launches += p->last_launches;
+        }
+        p->last_launches = launches;
+    }
     GR_CUDA(cudaMemcpyAsync(h_best, p->d_best, best_bytes, cudaMemcpyDeviceToHost, p->stream));
     GR_CUDA(cudaStreamSynchronize(p->stream));
     return GR_OK;
