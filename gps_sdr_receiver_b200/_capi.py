@@ -71,6 +71,7 @@ SIGNATURES = {
     "gr_get_chips": (C.c_int, [C.c_int, _P]),
     "gr_get_cacode": (C.c_int, [C.c_int, _P]),
     "gr_get_code_spectrum": (C.c_int, [C.c_int, _P]),
+    "gr_acq_classify_bins": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "gr_acq_plan_create": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "gr_acq_plan_destroy": (C.c_int, [_P]),
     "gr_acq_run_dev": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P]),

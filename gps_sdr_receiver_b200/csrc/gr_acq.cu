@@ -710,6 +710,31 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
 // ------------------------------------------------------------------------------------------
 #define GR_ACQ_G 4
 
+// Bins whose frequencies differ by a multiple of fs / 2048 = 1 kHz share ONE forward spectrum: the wipe-off factor
+// exp(-i 2 pi q 1000 (n + 1) / fs) = exp(-i 2 pi q (n + 1) / 2048) is the same in every 1-ms block, so it commutes with
+// the coherent fold and turns into a circular shift of the FFT by q bins (and a constant phase that |.| drops).  The
+// +-10 kHz / 500 Hz grid needs 2 forward FFTs per interval instead of 41, the 50-Hz grid 20 instead of 401.  The base
+// of a class is its canonical member in [-500, 500) Hz -- whether or not that frequency is itself a bin -- so that a
+// cell does not depend on which other bins are in the plan (bin-sharded searches stay bit-identical to unsharded ones)
+// and the float32 phase arguments are as small as they can be.
+extern "C" int gr_acq_classify_bins(const double* bin_hz, int nbins, int share, int32_t* base, int32_t* shift, double* base_hz) {
+    if (!bin_hz || !base || !shift || !base_hz || nbins < 1) { gr_set_error("gr_acq_classify_bins: invalid argument"); return GR_ERR_ARG; }
+    const double df = (double)GR_FS / GR_N;
+    int nb = 0;
+    for (int b = 0; b < nbins; ++b) {
+        const double q = share ? floor(bin_hz[b] / df + 0.5) : 0.0;
+        const double f0 = bin_hz[b] - q * df;
+        if (!(fabs(bin_hz[b]) < 0.5 * GR_FS)) { gr_set_error("gr_acq_classify_bins: bin %d out of range", b); return GR_ERR_ARG; }
+        int found = -1;
+        for (int i = 0; share && i < nb && found < 0; ++i)
+            if (fabs(f0 - base_hz[i]) < 1e-6) found = i;
+        if (found < 0) { found = nb; base_hz[nb++] = f0; }
+        base[b] = found;
+        shift[b] = (int32_t)((((long)q % GR_N) + GR_N) % GR_N);
+    }
+    return nb;
+}
+
 extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* bin_hz, int nbins, int tcoh_ms,
                                   int nnoncoh, int mode, int in_format, gr_acq_plan** plan) {
     GR_REQUIRE_INIT();
@@ -726,28 +751,11 @@ extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* b
     p->d_cells = nullptr; p->cells_bytes = 0; p->d_best = nullptr; p->best_bytes = 0;
     p->d_spec = nullptr; p->spec_bytes = 0;
     p->pipe_ready = false;
-    // Bins whose frequencies differ by a multiple of fs / 2048 = 1 kHz share ONE forward spectrum: the wipe-off factor
-    // exp(-i 2 pi q 1000 (n + 1) / fs) = exp(-i 2 pi q (n + 1) / 2048) is the same in every 1-ms block, so it commutes with
-    // the coherent fold and turns into a circular shift of the FFT by q bins (and a constant phase that |.| drops).  The
-    // +-10 kHz / 500 Hz grid needs 2 forward FFTs per interval instead of 41, the 50-Hz grid 20 instead of 401.  The base
-    // of a class is its canonical member in [-500, 500) Hz -- whether or not that frequency is itself a bin -- so that a
-    // cell does not depend on which other bins are in the plan (bin-sharded searches stay bit-identical to unsharded ones)
-    // and the float32 phase arguments are as small as they can be.  GPSB200_ACQ_NOSHARE=1: every bin its own base.
     std::vector<int32_t> bin_base(nbins), bin_shift(nbins);
-    std::vector<double> base_f;
-    const double df = (double)GR_FS / GR_N;
-    const bool share = getenv("GPSB200_ACQ_NOSHARE") == nullptr;
-    for (int b = 0; b < nbins; ++b) {
-        const double q = share ? floor(bin_hz[b] / df + 0.5) : 0.0;
-        const double f0 = bin_hz[b] - q * df;
-        if (fabs(q) >= GR_N / 2) { delete p; gr_set_error("gr_acq_plan_create: bin %d out of range", b); return GR_ERR_ARG; }
-        int found = -1;
-        for (size_t i = 0; share && i < base_f.size() && found < 0; ++i)
-            if (fabs(f0 - base_f[i]) < 1e-6) found = (int)i;
-        if (found < 0) { found = (int)base_f.size(); base_f.push_back(f0); }
-        bin_base[b] = found;
-        bin_shift[b] = (int32_t)((((long)q % GR_N) + GR_N) % GR_N);
-    }
+    std::vector<double> base_f(nbins);
+    const int nb = gr_acq_classify_bins(bin_hz, nbins, getenv("GPSB200_ACQ_NOSHARE") == nullptr, bin_base.data(), bin_shift.data(), base_f.data());
+    if (nb < 0) { delete p; return nb; }
+    base_f.resize(nb);
     p->nbase = (int)base_f.size();
     p->h_prns.assign(prns, prns + nprn);
     p->h_bin_code.resize(nbins);

@@ -81,6 +81,11 @@ typedef struct gr_acq_plan gr_acq_plan;
  * are circular shifts of each other); a cell's value does not depend on which other
  * bins the plan holds.  |bin_hz| must stay below fs/2.  Environment (read at creation):
  * GPSB200_ACQ_NOSHARE=1 one forward FFT per bin, as the reference computes it. */
+/* The classification gr_acq_plan_create applies to its Doppler bins (host only, needs no GPU): base[b] = index of the
+ * forward spectrum bin b uses, shift[b] = its circular shift in FFT bins (0..2047), base_hz[i] = frequency the i-th base
+ * spectrum is computed for (in [-500, 500) Hz when sharing is on).  Returns the number of base spectra or a negative
+ * error code.  share = 0: one spectrum per bin. */
+int gr_acq_classify_bins(const double* bin_hz, int nbins, int share, int32_t* base, int32_t* shift, double* base_hz);
 int gr_acq_plan_create(const int32_t* prns, int nprn, const double* bin_hz, int nbins,
                        int tcoh_ms, int nnoncoh, int mode, int in_format, gr_acq_plan** plan);
 int gr_acq_plan_destroy(gr_acq_plan* plan);
