@@ -116,3 +116,38 @@ def test_inverse_transform_data_flow_matches_the_circular_correlation():
     ref = N * np.fft.ifft(Y)
     np.testing.assert_allclose(np.abs(out), np.abs(ref), rtol=1e-9)
     np.testing.assert_allclose(out, ref.imag + 1j * ref.real, rtol=1e-9, atol=1e-9)   # fft(swap(y)) = swap(N ifft(y))
+
+
+def test_tmem_transpose_rounds_deliver_the_radix8_groups():
+    """The second transpose of the FFT goes through tensor memory (csrc/gr_fft2048t.cuh).  With the fragment layout measured
+    by tools/ubench/tmem_probe.cu (profiles/tmem_probe_r01.log) --
+        tcgen05.st.16x256b.x4, thread T, register 16 b + 4 i + 2 r + q  ->  lane 16 b + 8 r + T / 4, column 8 i + 2 (T % 4) + q
+        tcgen05.ld.32x32b,     thread L, register c                     <-  lane L, column c
+    -- two store / load rounds with the kernel's register order must leave, in lane L, the eight n3 inputs of the two
+    radix-8 groups (k1loc(L), k2lo(L) + 8 h) in complex registers 8 h + 4 (n3 & 1) + 2 (n3 >> 2) + ((n3 >> 1) & 1)."""
+    def one_round(regs):                                    # regs[T][rho] -> new[L][c]
+        new = [[None] * 32 for _ in range(32)]
+        for T in range(32):
+            for rho in range(32):
+                b, i, r, q = rho >> 4, (rho >> 2) & 3, (rho >> 1) & 1, rho & 1
+                lane, col = 16 * b + 8 * r + T // 4, 8 * i + 2 * (T % 4) + q
+                assert new[lane][col] is None
+                new[lane][col] = regs[T][rho]
+        return new
+
+    regs = [[None] * 32 for _ in range(32)]
+    for T in range(32):                                     # stage-2 thread: n3 = (T >> 1) & 7, k1loc = 2 (T >> 4) + (T & 1)
+        n3, k1loc = (T >> 1) & 7, 2 * (T >> 4) + (T & 1)
+        for k2 in range(16):
+            K = 8 * ((k2 >> 2) & 1) + 4 * ((k2 >> 1) & 1) + 2 * ((k2 >> 3) & 1) + (k2 & 1)     # (e2 e1 e3 e0)
+            regs[T][2 * K] = (k1loc, n3, k2, "re")
+            regs[T][2 * K + 1] = (k1loc, n3, k2, "im")
+    regs = one_round(one_round(regs))
+    for L in range(32):
+        k1loc = 2 * (L & 1) + ((L >> 3) & 1)
+        k2lo = 4 * ((L >> 2) & 1) + 2 * ((L >> 4) & 1) + ((L >> 1) & 1)
+        for h in range(2):
+            for n3 in range(8):
+                K = 8 * h + 4 * (n3 & 1) + 2 * (n3 >> 2) + ((n3 >> 1) & 1)
+                assert regs[L][2 * K] == (k1loc, n3, k2lo + 8 * h, "re"), (L, h, n3, regs[L][2 * K])
+                assert regs[L][2 * K + 1] == (k1loc, n3, k2lo + 8 * h, "im")
