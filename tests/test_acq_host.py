@@ -151,3 +151,43 @@ def test_tmem_transpose_rounds_deliver_the_radix8_groups():
                 K = 8 * h + 4 * (n3 & 1) + 2 * (n3 >> 2) + ((n3 >> 1) & 1)
                 assert regs[L][2 * K] == (k1loc, n3, k2lo + 8 * h, "re"), (L, h, n3, regs[L][2 * K])
                 assert regs[L][2 * K + 1] == (k1loc, n3, k2lo + 8 * h, "im")
+
+
+def test_shared_spectra_identity_against_the_oracle():
+    """The identity behind the shared forward spectra, checked against the oracle (the reference's per-bin float32 wipe-off,
+    gpsrecv.py:232-235) on the CPU: the coherent spectrum of bin f0 + q kHz is the spectrum of bin f0 rotated by q FFT
+    bins, up to a constant phase, for 1-ms and for 10-ms coherent intervals; the cells of the rotated form agree with the
+    oracle's grid within the magnitude tolerance."""
+    from oracle import gps_oracle as orc
+    from gps_sdr_receiver_b200 import synth
+    sats = [synth.Sat(prn=9, doppler=3270.0, delay=700.3, amp=0.09), synth.Sat(prn=23, doppler=-1240.0, delay=50.8, amp=0.09)]
+    for tcoh, k in ((1, 4), (10, 2)):
+        n_ms = tcoh * k
+        data = orc.raw_to_complex(synth.make_iq(sats, n_ms, seed=8))
+        n = n_ms * 2048
+        t = orc.sec_time(n)
+        f_base = -250.0                                              # canonical member of its class
+        xb, _ = orc.wipeoff(data, f_base, 0, n, t)
+        base = [orc.coherent_spectrum(xb, i * tcoh, tcoh) for i in range(k)]
+        for q in (-7, 0, 3, 9):
+            xq, _ = orc.wipeoff(data, f_base + 1000.0 * q, 0, n, t)
+            for i in range(k):
+                direct = orc.coherent_spectrum(xq, i * tcoh, tcoh)
+                rot = np.roll(base[i], -q)                           # rot[m] = base[m + q]
+                ph = np.vdot(rot, direct) / np.vdot(rot, rot)        # the constant phase factor
+                assert abs(abs(ph) - 1.0) < 1e-5
+                # what is left is the reference's own float32 rounding of the phase argument w t (it grows with |f| t:
+                # 6e-6 of the largest line at 9 kHz x 4 ms, 3e-5 at 9 kHz x 20 ms); the rotated form has the smaller arguments
+                assert np.abs(direct - ph * rot).max() < 1e-4 * np.abs(direct).max()
+        # cells: oracle grid at f_base + 1000 q vs statistics of the rotated base spectra
+        ref = orc.acq_grid(data, [9, 23], f_base + 3000.0, 1000.0, 1, tcoh, k, orc.ACQ_MODE_POW)
+        for i, p in enumerate((9, 23)):
+            cs = np.conjugate(orc.code_spectrum(p))
+            stat = np.zeros(2048)
+            for s in base:
+                c = np.fft.ifft(np.roll(s, -3) * cs)
+                stat += c.real ** 2 + c.imag ** 2
+            st = orc.acq_cell_stats(stat)
+            assert int(st["mx"]) == int(ref["mx"][i, 0])
+            for key in ("peak", "mean", "std", "z"):
+                assert abs(st[key] - ref[key][i, 0]) <= 1e-4 * abs(ref[key][i, 0]), (tcoh, p, key)
