@@ -19,9 +19,24 @@ def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
+def classify_bins(bin_hz, share: bool = True):
+    """The 1-kHz classes an AcqPlan forms from its Doppler bins (host only, `gr_acq_classify_bins`): bins that differ by
+    a multiple of fs / 2048 share one forward FFT and differ by a circular shift of it.  Returns (base index per bin,
+    shift in FFT bins per bin, base frequencies)."""
+    b = np.ascontiguousarray(bin_hz, dtype=np.float64)
+    base = np.zeros(b.size, np.int32)
+    shift = np.zeros(b.size, np.int32)
+    base_hz = np.zeros(b.size, np.float64)
+    n = _capi.lib().gr_acq_classify_bins(b.ctypes.data, b.size, 1 if share else 0, base.ctypes.data, shift.ctypes.data,
+                                         base_hz.ctypes.data)
+    _capi.check(min(n, 0))
+    return base, shift, base_hz[:n]
+
+
 class AcqPlan:
     """A fixed search grid: `prns` x `bin_hz`, `tcoh_ms` coherent milliseconds
-    (gpsrecv.py:250-254), `nnoncoh` non-coherent accumulations."""
+    (gpsrecv.py:250-254), `nnoncoh` non-coherent accumulations.  Bins 1 kHz apart share one
+    forward spectrum (see `classify_bins`); a cell does not depend on the other bins of the plan."""
 
     def __init__(self, prns, bin_hz, tcoh_ms: int, nnoncoh: int = 1, mode: int = GR_ACQ_POW,
                  in_format: int = GR_IN_U8IQ, device: int = 0):

@@ -6,28 +6,26 @@ hardware-specific part (the tensor-memory fragment layout of the second transpos
 implements; everything else is the kernel's own index arithmetic."""
 from __future__ import annotations
 
-import ctypes as C
-
 import numpy as np
 import pytest
 
 
 @pytest.fixture(scope="module")
 def lib():
-    from gps_sdr_receiver_b200 import _build, _capi
+    from gps_sdr_receiver_b200 import _build
     _build.build()
-    return _capi.raw_lib() if hasattr(_capi, "raw_lib") else C.CDLL(_build.LIB)
+    return None
 
 
 def _classify(lib, bins, share=1):
-    bins = np.asarray(bins, dtype=np.float64)
-    base = np.zeros(bins.size, np.int32)
-    shift = np.zeros(bins.size, np.int32)
-    base_hz = np.zeros(bins.size, np.float64)
-    lib.gr_acq_classify_bins.restype = C.c_int
-    lib.gr_acq_classify_bins.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-    n = lib.gr_acq_classify_bins(bins.ctypes.data, bins.size, share, base.ctypes.data, shift.ctypes.data, base_hz.ctypes.data)
-    return n, base, shift, base_hz[:max(n, 0)]
+    """(number of base spectra or -1, base index per bin, shift per bin, base frequencies) through the Python mirror."""
+    from gps_sdr_receiver_b200 import _capi
+    from gps_sdr_receiver_b200.acquisition import classify_bins
+    try:
+        base, shift, base_hz = classify_bins(bins, share=bool(share))
+    except _capi.GrError:
+        return -1, None, None, None
+    return len(base_hz), base, shift, base_hz
 
 
 def test_bin_classes_of_the_baseline_grids(lib):

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Development harness: time the acquisition kernel pair on the config-2 grid and (optionally) compare the cells
-with a saved run -- the check used while the inverse kernel went through its generations (all of which were
-bit-identical to the first):
+with a saved run -- the check used while the inverse kernel went through its generations (the scalar ones are
+bit-identical to each other; the packed / shared-spectra forms differ by rounding, < 2e-5 relative on peaks).
+Switches: GPSB200_ACQ_SCALAR=1, GPSB200_ACQ_NOSHARE=1, GPSB200_ACQ_CTAS=1..3:
 
     python tools/acq_time.py [recs] [steps] [--save ref.npy | --compare ref.npy]
 """
