@@ -30,6 +30,7 @@
 struct gr_acq_plan {
     int nprn, nbins, tcoh, nnoncoh, mode, in_format;
     int nbase;             // distinct forward spectra per (recording, interval): bins 1 kHz apart share one, see gr_acq_plan_create
+    int exact_nco;         // GPSB200_ACQ_EXACT_NCO: the reference's float32 phase argument for EVERY sample of every bin
     int32_t* d_prns;
     float* d_w32;          // fl32(2*pi*f) per BASE bin (python-float product rounded once, gpsrecv.py:233)
     int32_t* d_bin_base;   // [nbins] base spectrum of a bin
@@ -59,6 +60,7 @@ struct AcqArgs {
     const int32_t* bin_shift;
     int nrec, nprn, nbins, nbase, ngroups, tcoh, nnoncoh, mode;
     int nchunks, bins_per_chunk;   // forward kernel: base bins per CTA
+    int exact_nco;                 // per-sample float32 phase arguments also for tcoh > 1 (see acq_fwd_kernel)
     float scale;               // 1 / (tcoh * 2048)
     // PRN list and (base << 16 | shift) per bin in the kernel parameters when they fit: the inverse kernel looks them up
     // at job boundaries, where a global load would be an exposed L2 round trip (in_params = 0: use the arrays above)
@@ -161,6 +163,23 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
             // sin/cos per thread and bin instead of 16 tcoh, and the fold is ONE complex FMA per sample.  (The float32
             // rounding of the reference's per-sample phase argument, up to 3e-5 rad, is then not reproduced sample by
             // sample; the effect on the correlation is below 1e-6 relative.)
+            if (a.exact_nco) {
+                // reference-exact form (GPSB200_ACQ_EXACT_NCO): every sample of every block gets the reference's own float32
+                // argument fl32(w32 * fl32((n + 1) / fs)), tcoh x more sin / cos.  For searches whose |w t| is so large
+                // (10 kHz x 200 ms = 1.2e4 rad, ulp 1e-3 rad) that the reference's rounding noise exceeds the 1e-4 tolerance.
+#pragma unroll
+                for (int j = 0; j < 16; ++j) X[j] = cf{0.f, 0.f};
+                for (int i = 0; i < a.tcoh; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const long long n = base0 + (long long)i * GR_N + 128 * j;
+                        const cf x = load_sample<IN_FMT>(src, n);
+                        const cf e = nco_fast(nco_arg(w32, n));
+                        X[j].x += x.x * e.x - x.y * e.y;
+                        X[j].y += x.y * e.x + x.x * e.y;
+                    }
+                }
+            } else {
             for (int i = t; i < a.tcoh; i += GR_FFT_THREADS)
                 Rtab[i] = nco_fast(__fmul_rn(w32, __fdiv_rn((float)(i * GR_N), GR_FS)));
             __syncthreads();
@@ -179,6 +198,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) X[j] = cmul(X[j], nco_fast(nco_arg(w32, base0 + 128 * j)));
+            }
         }
         fft2048<true>(X, smem, tw1, tw2, t);
         // two copies in natural order, E0[m] = X[m] and E1[m] = X[m + 1]: the inverse kernel fetches a spectrum rotated by
@@ -753,7 +773,9 @@ extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* b
     p->pipe_ready = false;
     std::vector<int32_t> bin_base(nbins), bin_shift(nbins);
     std::vector<double> base_f(nbins);
-    const int nb = gr_acq_classify_bins(bin_hz, nbins, getenv("GPSB200_ACQ_NOSHARE") == nullptr, bin_base.data(), bin_shift.data(), base_f.data());
+    p->exact_nco = getenv("GPSB200_ACQ_EXACT_NCO") != nullptr;      // implies one spectrum per bin (the reference's w32 per bin)
+    const int nb = gr_acq_classify_bins(bin_hz, nbins, getenv("GPSB200_ACQ_NOSHARE") == nullptr && !p->exact_nco, bin_base.data(),
+                                        bin_shift.data(), base_f.data());
     if (nb < 0) { delete p; return nb; }
     base_f.resize(nb);
     p->nbase = (int)base_f.size();
@@ -854,6 +876,7 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         a.bin_base = p->d_bin_base;
         a.bin_shift = p->d_bin_shift;
         a.nbase = p->nbase;
+        a.exact_nco = p->exact_nco;
         a.nrec = nr;
         a.nprn = p->nprn;
         a.nbins = p->nbins;

@@ -80,7 +80,9 @@ typedef struct gr_acq_plan gr_acq_plan;
  * Bins that differ by a multiple of fs/2048 = 1 kHz share one forward FFT (their spectra
  * are circular shifts of each other); a cell's value does not depend on which other
  * bins the plan holds.  |bin_hz| must stay below fs/2.  Environment (read at creation):
- * GPSB200_ACQ_NOSHARE=1 one forward FFT per bin, as the reference computes it. */
+ * GPSB200_ACQ_NOSHARE=1 one forward FFT per bin, as the reference computes it;
+ * GPSB200_ACQ_EXACT_NCO=1 additionally the reference's float32 phase argument for every
+ * sample also when tcoh_ms > 1 (slower forward kernel; for searches with |2 pi f t| ~ 1e4). */
 /* The classification gr_acq_plan_create applies to its Doppler bins (host only, needs no GPU): base[b] = index of the
  * forward spectrum bin b uses, shift[b] = its circular shift in FFT bins (0..2047), base_hz[i] = frequency the i-th base
  * spectrum is computed for (in [-500, 500) Hz when sharing is on).  Returns the number of base spectra or a negative

@@ -222,6 +222,26 @@ def test_fine_grid_at_the_band_edge_over_200_ms_vs_oracle(gpu):
         assert int(cells["mx"][i, b]) == int(ref["mx"][i, b]) and (int(cells["mx"][i, b]) - int(sats[i].delay)) % 2048 in (0, 1)
 
 
+def test_band_edge_reference_exact_nco_meets_the_tolerance_on_every_lag(gpu, monkeypatch):
+    """The same corner with GPSB200_ACQ_EXACT_NCO=1: one forward spectrum per bin and the reference's own float32 phase
+    argument fl32(w32 * fl32((n + 1) / fs)) for every sample of every block (tcoh x more sin / cos in the forward kernel).
+    Then every checked quantity -- peak, mean, std, z, neighbours, second peak -- is within 1e-4 of the oracle."""
+    from gps_sdr_receiver_b200 import synth
+    from gps_sdr_receiver_b200.acquisition import AcqPlan, GR_ACQ_POW
+    sats = [synth.Sat(prn=12, doppler=9490.0, delay=611.4, amp=0.02, bit_offset_ms=7, bit_seed=3),
+            synth.Sat(prn=25, doppler=-9510.0, delay=1490.7, amp=0.02, bit_offset_ms=15, bit_seed=4)]
+    raw = synth.make_iq(sats, 200, seed=12)
+    data = orc.raw_to_complex(raw)
+    monkeypatch.setenv("GPSB200_ACQ_EXACT_NCO", "1")
+    for f0 in (9400.0, -9600.0):
+        bins = [f0 + 50.0 * b for b in range(5)]
+        cells = AcqPlan([12, 25], bins, 10, 20, GR_ACQ_POW).run(raw)[0]
+        ref = orc.acq_grid(data, [12, 25], f0, 50.0, len(bins), 10, 20, orc.ACQ_MODE_POW)
+        _check_cells(cells, ref)
+        assert np.array_equal(cells["mx"], ref["mx"])
+    monkeypatch.delenv("GPSB200_ACQ_EXACT_NCO")
+
+
 def test_ragged_and_invalid_inputs(gpu):
     from gps_sdr_receiver_b200 import _capi
     from gps_sdr_receiver_b200.acquisition import AcqPlan
