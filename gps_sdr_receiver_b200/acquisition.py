@@ -149,6 +149,8 @@ def _cached_plan(prns, bins, tcoh, nnoncoh, mode, fmt) -> AcqPlan:
     p = _PLAN_CACHE.get(key)
     if p is None:
         if len(_PLAN_CACHE) > 64:
+            for old in _PLAN_CACHE.values():          # free the device memory now, not whenever __del__ runs
+                old.close()
             _PLAN_CACHE.clear()
         p = _PLAN_CACHE[key] = AcqPlan(prns, bins, tcoh, nnoncoh, mode, fmt)
     return p

@@ -47,6 +47,11 @@ struct gr_acq_plan {
     cudaEvent_t ev_in[GR_ACQ_HOST_CHUNKS];
     bool pipe_ready;
     int last_launches;
+    // The scratch above (d_spec, d_cells) belongs to the plan, so two *_dev calls of one plan must not overlap: a call on
+    // another stream than the previous one first makes its stream wait for the event recorded behind the previous call.
+    cudaEvent_t ev_last;
+    cudaStream_t last_stream;
+    bool has_last;
 };
 
 #define GR_ACQ_MAX_PRN_C 64
@@ -794,6 +799,10 @@ extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* b
     GR_CUDA(cudaMemcpy(p->d_bin_base, bin_base.data(), nbins * sizeof(int32_t), cudaMemcpyHostToDevice));
     GR_CUDA(cudaMemcpy(p->d_bin_shift, bin_shift.data(), nbins * sizeof(int32_t), cudaMemcpyHostToDevice));
     GR_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    GR_CUDA(cudaEventCreateWithFlags(&p->ev_last, cudaEventDisableTiming));
+    p->has_last = false;
+    p->last_stream = nullptr;
+    gr_lib()->live_handles += 1;
     *plan = p;
     return GR_OK;
 }
@@ -814,6 +823,8 @@ extern "C" int gr_acq_plan_destroy(gr_acq_plan* p) {
         for (int i = 0; i < GR_ACQ_HOST_CHUNKS; ++i) cudaEventDestroy(p->ev_in[i]);
     }
     cudaStreamDestroy(p->stream);
+    cudaEventDestroy(p->ev_last);
+    gr_lib()->live_handles -= 1;
     delete p;
     return GR_OK;
 }
@@ -846,6 +857,8 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
     int rc = grow((void**)&p->d_spec, &p->spec_bytes, (size_t)sub * spec_per_rec);
     if (rc != GR_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
+    GR_CUDA(cudaSetDevice(gr_lib()->device));
+    if (p->has_last && p->last_stream != s) GR_CUDA(cudaStreamWaitEvent(s, p->ev_last, 0));   // plan-owned scratch: calls of one plan serialise
     const bool one = p->tcoh == 1;
     void (*fwd)(const AcqArgs) = p->in_format == GR_IN_U8IQ ? (one ? acq_fwd_kernel<GR_IN_U8IQ, true> : acq_fwd_kernel<GR_IN_U8IQ, false>)
                                                             : (one ? acq_fwd_kernel<GR_IN_CF32, true> : acq_fwd_kernel<GR_IN_CF32, false>);
@@ -905,6 +918,9 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         GR_CUDA(cudaGetLastError());
         p->last_launches += 2;
     }
+    GR_CUDA(cudaEventRecord(p->ev_last, s));
+    p->last_stream = s;
+    p->has_last = true;
     return GR_OK;
 }
 
@@ -969,6 +985,7 @@ extern "C" int gr_acq_search_dev(gr_acq_plan* p, const void* d_samples, int nrec
     acq_best_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->d_cells, p->d_prns, nrec, p->nprn, p->nbins, d_best);
     GR_CUDA(cudaGetLastError());
     p->last_launches += 1;
+    GR_CUDA(cudaEventRecord(p->ev_last, (cudaStream_t)stream));      // d_cells is read by acq_best_kernel
     return GR_OK;
 }
 

@@ -11,6 +11,7 @@ struct GrLib {
     bool host_tables = false;
     int device = -1;
     int num_sms = 0;
+    int live_handles = 0;        // acquisition plans + tracking banks alive (they pin the library to its device)
     GrTables tab{};
     int8_t chips[GR_MAX_PRN + 1][1023];
     double code[GR_MAX_PRN + 1][GR_N];

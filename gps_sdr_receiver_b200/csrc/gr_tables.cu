@@ -13,7 +13,7 @@
 #include "gr_internal.h"
 
 static GrLib g_lib;
-static char g_err[512] = "";
+static thread_local char g_err[512] = "";      // per calling thread, like errno
 
 GrLib* gr_lib() { return &g_lib; }
 
@@ -25,7 +25,7 @@ void gr_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* gr_last_error(void) { return g_err; }
-extern "C" int gr_version(void) { return 100; }
+extern "C" int gr_version(void) { return 200; }
 
 // G2 output taps for PRN 1..37 (IS-GPS-200, table 3-Ia).
 static const int kG2Taps[GR_MAX_PRN][2] = {
@@ -89,6 +89,12 @@ static void fft_host(std::vector<std::complex<double>>& a) {
 extern "C" int gr_init(int device) {
     GrLib* L = gr_lib();
     if (L->ready && L->device == device) return GR_OK;
+    if (L->ready && L->live_handles > 0) {
+        // plans and banks hold device memory and use the tables of the device they were created on: one GPU per process
+        gr_set_error("gr_init: library is bound to device %d with %d live plan/bank handle(s); destroy them first "
+                     "(one GPU per process: run one process per GPU)", L->device, L->live_handles);
+        return GR_ERR_STATE;
+    }
     if (L->ready) gr_shutdown();
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);

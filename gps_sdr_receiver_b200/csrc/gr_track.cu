@@ -71,10 +71,13 @@ struct gr_track_bank {
     GrChan* d_state;
     int32_t* d_slots;
     std::vector<int> slot_used;      // host mirror
+    std::vector<int> slot_rec;       // recording index of each used slot
     std::vector<int> active;         // sorted active slots
     bool slots_dirty;
     cudaStream_t stream;             // for the host entry point
-    cudaStream_t last_stream;
+    cudaEvent_t ev_last;             // recorded behind the last launch (on whatever stream the caller gave): host edits wait on it
+    bool in_flight;
+    int max_rec;                     // largest recording index among the active channels
     void* d_in;  size_t in_bytes;
     gr_epoch_out* d_out; size_t out_bytes;
     int last_launches;
@@ -334,20 +337,22 @@ __device__ __forceinline__ void st_init_sweep(GrChanHot* c, GrChan* g, const gr_
     c->df_len = 1; c->df_head = 0; g->df[0] = 0.f;
     c->sweep = 1;
 }
-// gpslib.py:1331-1339 corrQuality
+// gpslib.py:1331-1339 corrQuality: CORRLST.append(cpq); if len > CORRLST_NO: del CORRLST[0]; means of the whole list and
+// of its last NO_SEC entries, kept as exact integer running sums.  At n_cyc = 8 the list's capacity equals the ring's
+// (60 * 128), so the slot the new entry goes into can be the one that holds the oldest entry: both entries that leave a
+// sum are read BEFORE the store.
 __device__ __forceinline__ void st_corr_quality(GrChanHot* c, GrChan* g, double code_phase, int no_sec) {
     const int cap = 60 * no_sec;
-    const int8_t v = code_phase < 0.0 ? -1 : 1;
-    g->cl[(c->cl_head + c->cl_len) % GR_CL_CAP] = v;
-    c->cl_len += 1;
-    c->cl_sum += v;
-    c->cl_sum_last += v;
-    if (c->cl_len > no_sec) c->cl_sum_last -= g->cl[(c->cl_head + c->cl_len - 1 - no_sec) % GR_CL_CAP];
-    if (c->cl_len > cap) {
-        c->cl_sum -= g->cl[c->cl_head];
-        c->cl_head = (c->cl_head + 1) % GR_CL_CAP;
-        c->cl_len -= 1;
-    }
+    const int v = code_phase < 0.0 ? -1 : 1;
+    const int len = c->cl_len, head = c->cl_head;
+    const bool full = len + 1 > cap;                       // append, then pop the oldest
+    const int out_all = full ? (int)g->cl[head] : 0;
+    const int out_win = (len + 1 > no_sec) ? (int)g->cl[(head + len - no_sec) % GR_CL_CAP] : 0;
+    g->cl[(head + len) % GR_CL_CAP] = (int8_t)v;
+    c->cl_sum += v - out_all;
+    c->cl_sum_last += v - out_win;
+    if (full) c->cl_head = (head + 1) % GR_CL_CAP;
+    else c->cl_len = len + 1;
     c->corr_q = (double)c->cl_sum / (double)c->cl_len;
     const int nl = c->cl_len < no_sec ? c->cl_len : no_sec;
     c->corr_l = (double)c->cl_sum_last / (double)nl;
@@ -908,10 +913,13 @@ extern "C" int gr_track_bank_create(const gr_track_cfg* cfg, gr_track_bank** ban
     gr_track_bank* b = new gr_track_bank();
     b->cfg = *cfg;
     b->slot_used.assign(cfg->max_channels, 0);
+    b->slot_rec.assign(cfg->max_channels, 0);
     b->slots_dirty = true;
     b->d_in = nullptr; b->in_bytes = 0; b->d_out = nullptr; b->out_bytes = 0; b->last_launches = 0;
-    b->last_stream = nullptr;
+    b->in_flight = false;
+    b->max_rec = 0;
     b->pipe_ready = false;
+    GR_CUDA(cudaEventCreateWithFlags(&b->ev_last, cudaEventDisableTiming));
     GR_CUDA(cudaMalloc((void**)&b->d_state, sizeof(GrChan) * (size_t)cfg->max_channels));
     GR_CUDA(cudaMemset(b->d_state, 0, sizeof(GrChan) * (size_t)cfg->max_channels));
     GR_CUDA(cudaMalloc((void**)&b->d_slots, sizeof(int32_t) * (size_t)cfg->max_channels));
@@ -922,6 +930,7 @@ extern "C" int gr_track_bank_create(const gr_track_cfg* cfg, gr_track_bank** ban
                                  (int)(track_smem_bytes() + track_stage_bytes(GR_MAX_NCYC))));
     GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(track_smem_bytes() + track_stage_bytes(GR_MAX_NCYC))));
+    gr_lib()->live_handles += 1;
     *bank = b;
     return GR_OK;
 }
@@ -934,6 +943,8 @@ extern "C" int gr_track_bank_destroy(gr_track_bank* b) {
     if (b->d_in) cudaFree(b->d_in);
     if (b->d_out) cudaFree(b->d_out);
     cudaStreamDestroy(b->stream);
+    cudaEventDestroy(b->ev_last);
+    gr_lib()->live_handles -= 1;
     if (b->pipe_ready) {
         cudaStreamDestroy(b->s_in);
         cudaStreamDestroy(b->s_out);
@@ -944,8 +955,12 @@ extern "C" int gr_track_bank_destroy(gr_track_bank* b) {
 }
 
 static int bank_quiesce(gr_track_bank* b) {
-    // state edits from the host must not race a process call still in flight
-    GR_CUDA(cudaStreamSynchronize(b->last_stream));
+    // state edits from the host must not race a process call still in flight.  An event, not the caller's stream: the
+    // stream of the last gr_track_process_dev call may have been destroyed by its owner since.
+    if (b->in_flight) {
+        GR_CUDA(cudaEventSynchronize(b->ev_last));
+        b->in_flight = false;
+    }
     return GR_OK;
 }
 
@@ -961,7 +976,8 @@ extern "C" int gr_track_add(gr_track_bank* b, int rec, int prn, double freq, int
     if (slot < 0) { gr_set_error("gr_track_add: bank full (%d channels)", (int)b->slot_used.size()); return GR_ERR_STATE; }
     int rc = bank_quiesce(b);
     if (rc != GR_OK) return rc;
-    static GrChan c;                      // gpslib.py:1050-1091
+    std::vector<GrChan> staging(1);       // gpslib.py:1050-1091 (9 KB: off the stack, and not a shared static)
+    GrChan& c = staging[0];
     memset(&c, 0, sizeof(c));
     c.h.active = 1; c.h.prn = prn; c.h.rec = rec; c.h.delay = delay;
     c.h.freq = freq; c.h.freq_weak = 1;
@@ -972,6 +988,7 @@ extern "C" int gr_track_add(gr_track_bank* b, int rec, int prn, double freq, int
     c.h.prev_stream_no = 0;
     GR_CUDA(cudaMemcpy(b->d_state + slot, &c, sizeof(GrChan), cudaMemcpyHostToDevice));
     b->slot_used[slot] = 1;
+    b->slot_rec[slot] = rec;
     b->slots_dirty = true;
     return slot;
 }
@@ -982,6 +999,8 @@ extern "C" int gr_track_remove(gr_track_bank* b, int slot) {
         gr_set_error("gr_track_remove: invalid slot %d", slot);
         return GR_ERR_ARG;
     }
+    int rc = bank_quiesce(b);             // a launch still running reads this slot's state: let it finish before the slot can be re-used
+    if (rc != GR_OK) return rc;
     b->slot_used[slot] = 0;
     b->slots_dirty = true;
     return GR_OK;
@@ -1018,18 +1037,26 @@ extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int
         return GR_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    GR_CUDA(cudaSetDevice(gr_lib()->device));
     if (b->slots_dirty) {
         b->active.clear();
+        b->max_rec = 0;
         for (size_t i = 0; i < b->slot_used.size(); ++i)
-            if (b->slot_used[i]) b->active.push_back((int)i);
+            if (b->slot_used[i]) { b->active.push_back((int)i); if (b->slot_rec[i] > b->max_rec) b->max_rec = b->slot_rec[i]; }
         if (!b->active.empty()) {
-            GR_CUDA(cudaStreamSynchronize(b->last_stream));
+            int rcq = bank_quiesce(b);
+            if (rcq != GR_OK) return rcq;
             GR_CUDA(cudaMemcpy(b->d_slots, b->active.data(), b->active.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         }
         b->slots_dirty = false;
     }
     b->last_launches = 0;
     if (b->active.empty()) return GR_OK;
+    if (b->max_rec > 0 && rec_stride < (int64_t)n_epochs * b->cfg.n_cyc * GR_N) {
+        gr_set_error("gr_track_process_dev: channels on recordings 0..%d need rec_stride >= %lld samples", b->max_rec,
+                     (long long)n_epochs * b->cfg.n_cyc * GR_N);
+        return GR_ERR_ARG;
+    }
     TrackArgs a;
     a.samples = d_samples;
     a.rec_stride = rec_stride;
@@ -1047,7 +1074,7 @@ extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int
     a.buf_bytes = GR_TRACK_BUF_BYTES;
     a.part_rows = GR_PART_ROWS;
     // dense form when the launch has more channels than fit at two CTAs per SM and the epoch is short enough for three
-    const char* dense_env = getenv("GPSB200_TRACK_DENSE");          // development / test switch: 0 = never, 1 = whenever it fits
+    const char* dense_env = getenv("GPSB200_TRACK_DENSE");          // development / test switch: 0 = never, 1 = whenever it fits (a getenv per launch, ~50 ns: the tests flip it between banks)
     const size_t dense_smem = track_smem_bytes(track_dense_buf_bytes(b->cfg.n_cyc)) + track_stage_bytes(b->cfg.n_cyc);
     const bool dense = a.stage && 3 * (dense_smem + 1024) <= 227 * 1024 &&
                        (dense_env ? atoi(dense_env) != 0 : a.n_active > 2 * gr_lib()->num_sms);
@@ -1062,7 +1089,8 @@ extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int
     else
         track_kernel<GR_IN_CF32, false><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);
     GR_CUDA(cudaGetLastError());
-    b->last_stream = s;
+    GR_CUDA(cudaEventRecord(b->ev_last, s));
+    b->in_flight = true;
     b->last_launches = 1;
     return GR_OK;
 }
@@ -1085,6 +1113,11 @@ extern "C" int gr_track_process_host(gr_track_bank* b, const void* h_samples, in
     if (nrec > 1 && (size_t)rec_stride < span) { gr_set_error("gr_track_process_host: rec_stride too short"); return GR_ERR_ARG; }
     const int nact = gr_track_num_active(b);
     if (nact == 0) return GR_OK;
+    for (size_t i = 0; i < b->slot_used.size(); ++i)
+        if (b->slot_used[i] && b->slot_rec[i] >= nrec) {
+            gr_set_error("gr_track_process_host: slot %d tracks recording %d, but the call holds %d recording(s)", (int)i, b->slot_rec[i], nrec);
+            return GR_ERR_ARG;
+        }
     // chunk: about 16 MiB of samples over all recordings, at least one epoch
     size_t ce = (16u << 20) / (ngps * bps * (size_t)nrec);
     if (ce < 1) ce = 1;

@@ -70,14 +70,19 @@ class FileReceiver:
         self.ngps = self.n_cyc * glob.CODE_SAMPLES
         self.found: list[tuple[float, int, float, int]] = []          # (z, prn, freq, delay) like gpsrecv.foundSats
 
-    def _cold_start(self, first_block: np.ndarray):
+    ACQ_TCOH_MS, ACQ_NNONCOH = 10, 2                                   # fine cold-start search: 20 ms of samples
+
+    def _cold_start(self, lead: np.ndarray):
+        """`lead`: the first streams of the recording, at least ACQ_TCOH_MS * ACQ_NNONCOH ms of samples."""
         from .acquisition import AcqPlan, GR_ACQ_POW
         from .batch import select_sats
         prns = list(range(1, 33))
         bins = [glob.MIN_FREQ + 50.0 * b for b in range(int((glob.MAX_FREQ - glob.MIN_FREQ) / 50.0) + 1)]
-        plan = AcqPlan(prns, bins, 10, 2, GR_ACQ_POW, device=self.device)
-        best = plan.search(first_block[:2 * plan.rec_samples])[0]
-        plan.close()
+        plan = AcqPlan(prns, bins, self.ACQ_TCOH_MS, self.ACQ_NNONCOH, GR_ACQ_POW, device=self.device)
+        try:
+            best = plan.search(lead[:2 * plan.rec_samples])[0]
+        finally:
+            plan.close()
         self.found = sorted(((float(best[i]["cell"]["z"]), prns[i], bins[int(best[i]["bin"])], int(best[i]["cell"]["mx"]))
                              for i in select_sats(best, self.z_min, self.max_sat)), reverse=True)
 
@@ -85,17 +90,23 @@ class FileReceiver:
         """Yield (skippedData, frameLst, coPhLst) tuples, one per second of recording (gpsrecv.py:496-519)."""
         glob.set_n_cyc(self.n_cyc)
         blocks = read_streams(self.path, self.n_cyc, self.start)
-        first = next(blocks, None)
-        if first is None:
-            return
-        self._cold_start(first)
+        # the search window is 20 ms: one stream at N_CYC = 32, two at 16, three at 8 -- they are tracked afterwards like the rest
+        need = -(-self.ACQ_TCOH_MS * self.ACQ_NNONCOH * glob.CODE_SAMPLES // self.ngps)
+        lead = []
+        for b in blocks:
+            lead.append(b)
+            if len(lead) == need:
+                break
+        if len(lead) < need:
+            return                                                      # shorter than the search window: nothing to report
+        self._cold_start(np.concatenate(lead))
         if not self.found:
             return
         bank = TrackBank(self.n_cyc, len(self.found), device=self.device)
         streams = [SatStream(prn, f, delay=d, bank=bank, frame_decoder=FrameDecoder()) for _, prn, f, d in self.found]
         coph: dict = {}
         smp = self.ngps                                                # SMP_TIME of the first stream (gpsrecv.py:469-471)
-        pending = [first]
+        pending = lead
         try:
             while pending:
                 while len(pending) < self.chunk:

@@ -14,6 +14,8 @@ import math
 
 import numpy as np
 
+from . import glob
+
 C_LIGHT = 2.99792458e8
 MU = 3.986005e14                 # WGS-84 value used by GPS, m^3/s^2
 OMEGA_E = 7.2921151467e-5        # rad/s
@@ -158,11 +160,15 @@ class ChannelObservables:
     def ready(self) -> bool:
         return self.ref is not None and all(self.eph.get(f"have{i}") for i in (1, 2, 3)) and len(self.code_phase) > 0
 
-    def transmit_time(self, s_rx: float, n_avg: int = 8, centre_ms: float = 16.0) -> float:
+    def transmit_time(self, s_rx: float, n_avg: int = 8, centre_ms: float | None = None) -> float:
         """Satellite clock reading (time of week) of the signal that arrives at receiver sample time s_rx
         (SMP_TIME convention).  `centre_ms`: middle of the correlation window inside an epoch
         ((n_cyc - corr_avg) / 2 + corr_avg / 2 blocks, gpslib.py:1315-1327): the time the code phase refers to.
-        The code phases of the last `n_avg` epochs up to s_rx are each propagated to s_rx and averaged."""
+        Default: derived from this channel's N_CYC.  The code phases of the last `n_avg` epochs up to s_rx are each propagated to s_rx and averaged."""
+        if centre_ms is None:                                    # 16 ms at N_CYC = 32, 8 at 16, 4 at 8 (CORR_AVG = 8)
+            n_cyc = self.ngps // 2048
+            corr_avg = min(glob.CORR_AVG, n_cyc)
+            centre_ms = (n_cyc - corr_avg) // 2 + corr_avg / 2.0
         st_ref, t_ref = self.ref
         pts = [c for c in self.code_phase if c[0] + centre_ms * 2048.0 <= s_rx][-n_avg:]
         if not pts:
