@@ -119,13 +119,61 @@ class ClockSampler:
 
 
 # ---- CPU legs (the oracle: test infrastructure, used here only as the timed CPU baseline) -------------
-def _cpu_grid_worker(seed):
+def _cpu_make_input(seed):
     from gps_sdr_receiver_b200 import synth
+    return synth.make_iq(bench_sats(seed), NNONCOH * TCOH, seed=seed)
+
+
+def _cpu_grid_worker(raw):
+    """One full configs[1] grid on one core; `raw` = the recording's uint8 I/Q (synthesised outside the timed region)."""
     from oracle import gps_oracle as orc
-    raw = synth.make_iq(bench_sats(seed), NNONCOH * TCOH, seed=seed)
     t0 = time.perf_counter()
     g = orc.acq_grid(orc.raw_to_complex(raw), PRNS, BINS[0], 500.0, NBIN, TCOH, NNONCOH, orc.ACQ_MODE_POW)
     return time.perf_counter() - t0, float(g["z"].max())
+
+
+FINE_BINS = [-10000.0 + 50.0 * b for b in range(401)]
+FINE_TCOH, FINE_K = 10, 20
+_FINE_RAW = None
+
+
+def _cpu_fine_init(raw):
+    global _FINE_RAW
+    from oracle import gps_oracle as orc
+    _FINE_RAW = orc.raw_to_complex(raw)
+    orc.code_spectrum(1)
+
+
+def _cpu_fine_worker(bin_idx):
+    """The Doppler bins `bin_idx` of ONE configs[3] grid (32 PRN x 2048 lags each) on one core."""
+    from oracle import gps_oracle as orc
+    t0 = time.perf_counter()
+    zmax = 0.0
+    for b in bin_idx:
+        g = orc.acq_grid(_FINE_RAW, PRNS, FINE_BINS[b], 0.0, 1, FINE_TCOH, FINE_K, orc.ACQ_MODE_POW)
+        zmax = max(zmax, float(g["z"].max()))
+    return time.perf_counter() - t0, zmax
+
+
+def cpu_fine_baseline(raw: np.ndarray, min_seconds: float = 8.0):
+    """configs[3] on the host: ONE 200-ms recording, its 401 Doppler bins spread over all cores (the grid is what
+    shards; the reference itself searches in a single process)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    jobs = [list(range(w, len(FINE_BINS), workers)) for w in range(workers)]
+    with mp.get_context("spawn").Pool(workers, initializer=_cpu_fine_init, initargs=(raw,)) as pool:
+        pool.map(_cpu_fine_worker, [[0]] * workers)                # warm the workers
+        n, spent = 0, 0.0
+        while spent < min_seconds:
+            t0 = time.perf_counter()
+            pool.map(_cpu_fine_worker, jobs)
+            spent += time.perf_counter() - t0
+            n += 1
+    cells = NPRN * len(FINE_BINS) * NLAG
+    return {"value": n * cells / spent, "unit": "cells/s", "cores": workers, "kind": "port",
+            "sample": f"{n} full grid(s) (32 x 401 x 2048, 10 ms x 20) of one recording, bins interleaved over {workers} worker "
+                      f"processes, oracle/gps_oracle.acq_grid, {spent:.1f} s"}
 
 
 def cpu_acq_baseline(min_seconds: float = 10.0):
@@ -134,7 +182,7 @@ def cpu_acq_baseline(min_seconds: float = 10.0):
     orc.code_spectrum(1)
     n, spent = 0, 0.0
     while spent < min_seconds:
-        dt, _ = _cpu_grid_worker(100 + n)
+        dt, _ = _cpu_grid_worker(_cpu_make_input(100 + n))
         spent += dt
         n += 1
     return {"value": n * CELLS_PER_REC / spent, "unit": "cells/s", "cores": 1, "kind": "port",
@@ -192,11 +240,14 @@ def run_reference(args):
     workers = max(1, min(cores, 64))
     ctx = mp.get_context("spawn")
     with ctx.Pool(workers) as pool:
-        for w in range(args.warmup):
-            pool.map(_cpu_grid_worker, range(1000 + w * workers, 1000 + (w + 1) * workers))
+        # inputs are synthesised (in the workers) BEFORE the timed region: a step times the search only
+        warm = [pool.map(_cpu_make_input, range(1000 + w * workers, 1000 + (w + 1) * workers)) for w in range(args.warmup)]
+        inputs = [pool.map(_cpu_make_input, range(2000 + k * workers, 2000 + (k + 1) * workers)) for k in range(args.steps)]
+        for w in warm:
+            pool.map(_cpu_grid_worker, w)
         t0 = time.perf_counter()
         for k in range(args.steps):
-            pool.map(_cpu_grid_worker, range(2000 + k * workers, 2000 + (k + 1) * workers))
+            pool.map(_cpu_grid_worker, inputs[k])
         dt = time.perf_counter() - t0
     value = args.steps * workers * CELLS_PER_REC / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -346,7 +397,11 @@ def run_b200(args):
                      "traffic": R * (5.3 + 25.5 + 94.6 + 7.0) * 1e6 / 128,
                      "peak_source": f"measured in this run: register-resident FFMA chains on all SMs (gr_debug_fp32_peak); "
                                     f"theoretical at 1965 MHz = {FP32_PEAK_THEORY:.1f}",
+                     "traffic_source": "ncu --set full capture of 128 recordings (profiles/acq_r01_v8_ncu_summary.md), scaled to R",
                      "flop_per_cell": FLOP_PER_CELL, "ms_per_launch": ms_kernel,
+                     # what the kernels execute: 2 forward FFTs + wipe-offs per interval instead of the 41 the count credits
+                     "flop_executed": R * (FLOP_PER_REC - (NBIN - 2) * NNONCOH * (F_FFT + TCOH * 2048 * 8)),
+                     "achieved_executed": R * (FLOP_PER_REC - (NBIN - 2) * NNONCOH * (F_FFT + TCOH * 2048 * 8)) / (ms_kernel * 1e-3) / 1e12,
                      "note": "BASELINE prescribes the FP32 FFT-flop roofline for acquisition; algorithmic flops = 5 N log2 N per FFT of the "
                              "reference's algorithm (one forward FFT per Doppler bin and interval: 4 % of the count); the kernels run 2 "
                              "forward FFTs per interval and derive the other 39 bins as circular shifts"},
@@ -354,82 +409,155 @@ def run_b200(args):
 
     # ---------------- weak-signal fine acquisition (configs[3]): 10 ms x 20, 50 Hz bins, +-10 kHz ----------------
     if not args.skip_fine:
-        f_bins = [-10000.0 + 50.0 * b for b in range(401)]
-        f_tcoh, f_k, f_recs = 10, 20, args.fine_recs
+        from gps_sdr_receiver_b200 import multi
+        f_bins = FINE_BINS
+        f_tcoh, f_k, f_recs = FINE_TCOH, FINE_K, args.fine_recs
         f_flop = (len(f_bins) * f_k * F_FFT + NPRN * len(f_bins) * f_k * F_FFT + NPRN * len(f_bins) * f_k * 2048 * 10
                   + len(f_bins) * f_k * f_tcoh * 2048 * 8)
         f_cells = NPRN * len(f_bins) * NLAG
+        f_rec_bytes = 2 * f_tcoh * f_k * 2048
         fsats = [synth.Sat(prn=s.prn, doppler=s.doppler / 2.0, delay=s.delay, amp=0.02, phi0=s.phi0, bit_offset_ms=s.bit_offset_ms,
                            bit_seed=s.bit_seed) for s in sats]
         fraw = synth.make_iq_dev(fsats, f_recs * f_tcoh * f_k, noise_sigma=0.25, seed=4242 + rank, device=local)
-        fplan = AcqPlan(PRNS, f_bins, f_tcoh, f_k, GR_ACQ_POW, device=local)
         fbest_dev = torch.empty((f_recs, NPRN, ACQ_BEST.itemsize), dtype=torch.uint8, device=dev)
-        fb = AcqPlan.best_from_tensor(fplan.search_dev(fraw, nrec=f_recs, out=fbest_dev))
-        torch.cuda.synchronize()
-        for s in fsats:                                        # amp 0.02: far below the 1-ms detection limit
-            b = fb[0, s.prn - 1]
-            assert abs(f_bins[int(b["bin"])] - s.doppler) <= 75.0 and b["cell"]["z"] > 10, ("fine acquisition missed", s, b)
+
+        def fine_parity(plan):
+            """Untimed: a sub-grid of recording 0 of THIS run's data against the CPU oracle (peak / mean / std / z relative,
+            arg-max lag exact): the two band edges, the centre and the bins of two injected satellites x those two PRNs + two
+            PRNs that are not in the recording."""
+            from oracle import gps_oracle as orc
+            cells = AcqPlan.cells_from_tensor(plan.run_dev(fraw[:f_rec_bytes], nrec=1))[0]
+            data = orc.raw_to_complex(fraw[:f_rec_bytes].cpu().numpy())
+            absent = [p for p in PRNS if p not in {s_.prn for s_ in fsats}][:2]
+            prn_l = [fsats[0].prn, fsats[1].prn] + absent
+            bins_l = sorted({0, 200, 400} | {int(round((s_.doppler + 10000.0) / 50.0)) for s_ in fsats[:2]})
+            worst, mx_ok = 0.0, True
+            for b in bins_l:
+                g = orc.acq_grid(data, prn_l, f_bins[b], 0.0, 1, f_tcoh, f_k, orc.ACQ_MODE_POW)
+                for i, p_ in enumerate(prn_l):
+                    c = cells[p_ - 1, b]
+                    for k_ in ("peak", "mean", "std", "z"):
+                        worst = max(worst, abs(float(c[k_]) / float(g[k_][i, 0]) - 1.0))
+                    if float(g["z"][i, 0]) > 8:
+                        mx_ok = mx_ok and int(c["mx"]) == int(g["mx"][i, 0])
+            return {"max_rel_err_vs_oracle": worst, "argmax_equal_on_detections": bool(mx_ok),
+                    "checked": f"{len(bins_l)} bins x {len(prn_l)} PRNs x 2048 lags of recording 0 (peak, mean, std, z)"}
+
+        def time_fine(plan):
+            fb = AcqPlan.best_from_tensor(plan.search_dev(fraw, nrec=f_recs, out=fbest_dev))
+            torch.cuda.synchronize()
+            for s_ in fsats:                                       # amp 0.02: far below the 1-ms detection limit
+                b = fb[0, s_.prn - 1]
+                assert abs(f_bins[int(b["bin"])] - s_.doppler) <= 75.0 and b["cell"]["z"] > 10, ("fine acquisition missed", s_, b)
+            for _ in range(2):
+                plan.search_dev(fraw, nrec=f_recs, out=fbest_dev)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_a = time.perf_counter()
+            g0.record()
+            for i in range(args.steps):
+                plan.search_dev(fraw, nrec=f_recs, out=fbest_dev)
+            g1.record()
+            barrier()
+            windows.append((t_a, time.perf_counter()))
+            return max_over_ranks(g0.elapsed_time(g1)) / args.steps
+
+        fplan = AcqPlan(PRNS, f_bins, f_tcoh, f_k, GR_ACQ_POW, device=local)
+        ms_fine = time_fine(fplan)
+        # end to end: 16 recordings of 200 ms in pinned host memory -> tuples in host memory, every step
+        fhost = torch.empty(fraw.numel(), dtype=torch.uint8).pin_memory()
+        fhost.copy_(fraw)
+        fbest_host = torch.empty((f_recs, NPRN, ACQ_BEST.itemsize), dtype=torch.uint8).pin_memory()
+        fbest_np = fbest_host.numpy().view(ACQ_BEST).reshape(f_recs, NPRN)
+        for _ in range(2):
+            fplan.search(fhost.numpy(), nrec=f_recs, out=fbest_np)
         barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_a = time.perf_counter()
-        g0.record()
         for i in range(args.steps):
-            fplan.search_dev(fraw, nrec=f_recs, out=fbest_dev)
-        g1.record()
+            fplan.search(fhost.numpy(), nrec=f_recs, out=fbest_np)
+        t_fe2e = time.perf_counter() - t_a
         barrier()
         windows.append((t_a, time.perf_counter()))
-        ms_fine = max_over_ranks(g0.elapsed_time(g1)) / args.steps
+        t_fe2e = max_over_ranks(t_fe2e)
+        assert np.array_equal(fbest_np["bin"], AcqPlan.best_from_tensor(fbest_dev)["bin"])
         line["acq_fine"] = {
             "metric": METRIC, "value": world * f_recs * f_cells / (ms_fine * 1e-3), "unit": "cells/s", "ms_per_step": ms_fine,
+            "form": "default: one forward spectrum per 1-kHz class of bins, blocks 1..9 of a coherent interval rotated by one "
+                    "exp(-i w 2048 b / fs) per block (block 0 with the reference's float32 argument per sample)",
             "config": {"workload": "weak-signal fine acquisition 32 PRN x 401 Doppler (+-10 kHz, 50 Hz) x 2048 code phases, 10 ms coherent "
                                    "x 20 non-coherent (BASELINE configs[3]); every rank searches its own recordings",
                        "recordings_per_gpu_per_step": f_recs, "cells_per_recording": f_cells},
+            "e2e": {"value": world * f_recs * f_cells * args.steps / t_fe2e, "unit": "cells/s", "h2d_bytes_per_step": f_recs * f_rec_bytes,
+                    "d2h_bytes_per_step": f_recs * NPRN * ACQ_BEST.itemsize, "api": "AcqPlan.search -> gr_acq_search_host (C ABI), pinned host buffers"},
             "roofline": {"bound": "fp32", "achieved": f_recs * f_flop / (ms_fine * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": f_recs * f_flop / (ms_fine * 1e-3) / 1e12 / fp32_peak, "flop_per_cell": f_flop / f_cells},
+            "parity": fine_parity(fplan) if rank == 0 else None,
         }
-        launches += args.steps * 3
-        if world > 1:
-            # configs[3] as stated: ONE set of recordings, the Doppler bins of the search sharded across the ranks (strong
-            # scaling of one long search); NCCL all_gather of the per-shard tuples, merged by largest z / lowest bin
-            from gps_sdr_receiver_b200 import multi
-            mine = multi.partition(len(f_bins), world, rank)
-            sraw = synth.make_iq_dev(fsats, f_recs * f_tcoh * f_k, noise_sigma=0.25, seed=4242, device=local)   # same bytes on every rank
-            splan = AcqPlan(PRNS, [f_bins[b] for b in mine], f_tcoh, f_k, GR_ACQ_POW, device=local)
-            sbest = torch.empty((f_recs, NPRN, ACQ_BEST.itemsize), dtype=torch.uint8, device=dev)
-            sgath = torch.empty((world, f_recs, NPRN, ACQ_BEST.itemsize), dtype=torch.uint8, device=dev)
+        launches += (args.steps + 3) * 3 + (args.steps + 2) * 3
+        # the reference-exact form: the reference's own float32 phase argument for every sample of every bin
+        os.environ["GPSB200_ACQ_EXACT_NCO"] = "1"
+        eplan = AcqPlan(PRNS, f_bins, f_tcoh, f_k, GR_ACQ_POW, device=local)
+        del os.environ["GPSB200_ACQ_EXACT_NCO"]
+        ms_exact = time_fine(eplan)
+        line["acq_fine_exact"] = {
+            "metric": METRIC, "value": world * f_recs * f_cells / (ms_exact * 1e-3), "unit": "cells/s", "ms_per_step": ms_exact,
+            "form": "GPSB200_ACQ_EXACT_NCO=1: one forward spectrum per bin, fl32(w32 * fl32((n+1)/fs)) for every sample (gpsrecv.py:232-235)",
+            "roofline": {"bound": "fp32", "achieved": f_recs * f_flop / (ms_exact * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": f_recs * f_flop / (ms_exact * 1e-3) / 1e12 / fp32_peak},
+            "parity": fine_parity(eplan) if rank == 0 else None,
+        }
+        launches += (args.steps + 3) * 3
+        eplan.close()
+        fplan.close()
 
-            def sstep():
-                splan.search_dev(sraw, nrec=f_recs, out=sbest)
+        # configs[3] as stated: ONE set of recordings, the Doppler bins of the search sharded across the ranks (strong
+        # scaling of one long search), bins grouped by 1-kHz class so that a shard's forward work shrinks with it
+        # (multi.partition_bins); NCCL all_gather of the per-shard tuples, merged by largest z / lowest global bin.
+        # N = 1 runs the same code (one shard, no gather): the base of the curve.
+        lists = [multi.partition_bins(f_bins, world, r) for r in range(world)]
+        mine = lists[rank]
+        sraw = synth.make_iq_dev(fsats, f_recs * f_tcoh * f_k, noise_sigma=0.25, seed=4242, device=local)   # same bytes on every rank
+        splan = AcqPlan(PRNS, [f_bins[b] for b in mine], f_tcoh, f_k, GR_ACQ_POW, device=local)
+        sbest = torch.empty((f_recs, NPRN, ACQ_BEST.itemsize), dtype=torch.uint8, device=dev)
+        sgath = torch.empty((world, f_recs, NPRN, ACQ_BEST.itemsize), dtype=torch.uint8, device=dev)
+
+        def sstep():
+            splan.search_dev(sraw, nrec=f_recs, out=sbest)
+            if world > 1:
                 dist.all_gather_into_tensor(sgath, sbest)
+            else:
+                sgath[0].copy_(sbest)
 
-            for _ in range(args.warmup):
-                sstep()
-            torch.cuda.synchronize()
-            parts = [AcqPlan.best_from_tensor(sgath[r]) for r in range(world)]
-            merged = multi.merge_bin_shards(parts, [multi.partition(len(f_bins), world, r).start for r in range(world)])
-            for s_ in fsats:
-                b = merged[0, s_.prn - 1]
-                assert abs(f_bins[int(b["bin"])] - s_.doppler) <= 75.0 and b["cell"]["z"] > 10, ("sharded fine acquisition missed", s_, b)
-            barrier()
-            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t_a = time.perf_counter()
-            h0.record()
-            for i in range(args.steps):
-                sstep()
-            h1.record()
-            barrier()
-            windows.append((t_a, time.perf_counter()))
-            ms_sh = max_over_ranks(h0.elapsed_time(h1)) / args.steps
-            line["acq_fine_sharded"] = {
-                "metric": METRIC, "value": f_recs * f_cells / (ms_sh * 1e-3), "unit": "cells/s", "ms_per_step": ms_sh, "scaling": "strong",
-                "config": {"workload": "the same fine grid for ONE set of recordings, its 401 Doppler bins sharded across the ranks "
-                                       "(BASELINE configs[3]); NCCL all_gather of the per-shard tuples each step, merged on every rank",
-                           "recordings_per_step": f_recs, "bins_per_rank": len(mine), "cells_per_recording": f_cells},
-            }
-            launches += args.steps * 3
-            del sraw, splan
+        for _ in range(args.warmup):
+            sstep()
+        torch.cuda.synchronize()
+        parts = [AcqPlan.best_from_tensor(sgath[r]) for r in range(world)]
+        merged = multi.merge_bin_lists(parts, lists)
+        for s_ in fsats:
+            b = merged[0, s_.prn - 1]
+            assert abs(f_bins[int(b["bin"])] - s_.doppler) <= 75.0 and b["cell"]["z"] > 10, ("sharded fine acquisition missed", s_, b)
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_a = time.perf_counter()
+        h0.record()
+        for i in range(args.steps):
+            sstep()
+        h1.record()
+        barrier()
+        windows.append((t_a, time.perf_counter()))
+        ms_sh = max_over_ranks(h0.elapsed_time(h1)) / args.steps
+        line["acq_fine_sharded"] = {
+            "metric": METRIC, "value": f_recs * f_cells / (ms_sh * 1e-3), "unit": "cells/s", "ms_per_step": ms_sh, "scaling": "strong",
+            "config": {"workload": "the same fine grid for ONE set of recordings, its 401 Doppler bins sharded across the ranks by 1-kHz "
+                                   "class (BASELINE configs[3]); NCCL all_gather of the per-shard tuples each step, merged on every rank",
+                       "recordings_per_step": f_recs, "bins_per_rank": len(mine), "cells_per_recording": f_cells},
+        }
+        launches += (args.steps + args.warmup) * 3
+        splan.close()
+        del sraw
         line["gpu_launches"] = launches
-        del fraw, fplan
+        fine_raw_host = fraw[:f_rec_bytes].cpu().numpy() if rank == 0 else None
+        del fraw, fhost
 
     # ---------------- tracking (configs[2]) ----------------
     if not args.skip_tracking:
@@ -565,19 +693,77 @@ def run_b200(args):
                 "config": {"workload": f"{RB} recordings x {TRACK_NCH} channels per GPU, {secs:.0f} s each, 8-ms epochs, one launch "
                                        f"({RB * TRACK_NCH} channel CTAs, all resident: 3 per SM in the kernel's dense form; per-GPU share of BASELINE configs[4])"},
                 "roofline": {"bound": "hbm", "kernel": "track_kernel", "achieved": (b_raw + b_out) / t_batch / 1e9, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": (b_raw + b_out) / t_batch / 1e9 / hbm_peak, "traffic": None,
+                             "unit": "GB/s", "frac": (b_raw + b_out) / t_batch / 1e9 / hbm_peak,
+                             # dram__bytes_read + dram__bytes_write of the kernel, ncu --set full capture of 400 epochs x 384
+                             # channels (profiles/track_r01_dense_ncu_summary.md: 17.0 + 16.9 MB), scaled to this launch
+                             "traffic": nb_ep * RB * TRACK_NCH * (17.009152 + 16.938496) * 1e6 / (400 * 384),
+                             "traffic_source": "ncu capture (profiles/), scaled by channel-epochs",
                              "fp32_achieved_tflops": nb_ep * RB * TRACK_NCH * flop_ce / t_batch / 1e12, "fp32_peak_tflops": fp32_peak,
                              "note": "algorithmic bytes = each recording's raw I/Q once + one record per channel-epoch; the kernel is "
                                      "FP32/latency-bound (about 260 flop per byte, DESIGN.md 4.3), so the HBM fraction stays small by construction"},
             }
             line["gpu_launches"] += 1
-            del brec, bout
+            del bout
+
+            # ---- configs[4] per GPU: acquisition -> hand-over -> tracking -> NCCL gather of the per-stream results ----
+            from gps_sdr_receiver_b200.batch import BatchReceiver, gather_stream_results
+            rx = BatchReceiver(n_cyc=TRACK_NCYC, max_sat=TRACK_NCH, device=local)
+            rec_samples = span
+
+            def pipeline(host_tensor=None):
+                res = rx.run_host(host_tensor, RB, rec_samples, rec0=rank * RB) if host_tensor is not None \
+                    else rx.run_local(brec, RB, rec_samples, rec0=rank * RB)
+                return gather_stream_results(res, device=dev) if world > 1 else res
+
+            res = pipeline()                                        # warm-up + validity
+            want = {s_.prn for s_ in tsats}
+            for r_ in range(rank * RB, (rank + 1) * RB):
+                got = {int(x["prn"]) for x in res[res["rec"] == r_] if x["locked"] == 1 and x["sweep"] == 0}
+                assert got == want, ("batch pipeline lost a satellite", r_, sorted(got), sorted(want))
+            barrier()
+            t_a = time.perf_counter()
+            res = pipeline()
+            torch.cuda.synchronize()
+            t_pipe = time.perf_counter() - t_a
+            barrier()
+            windows.append((t_a, time.perf_counter()))
+            t_pipe = max_over_ranks(t_pipe)
+            n_streams = int(res.size)
+            hb = torch.empty(brec.numel(), dtype=torch.uint8).pin_memory()
+            hb.copy_(brec)
+            del brec
+            pipeline(hb)
+            barrier()
+            t_a = time.perf_counter()
+            res_h = pipeline(hb)
+            torch.cuda.synchronize()
+            t_pipe_h = time.perf_counter() - t_a
+            barrier()
+            windows.append((t_a, time.perf_counter()))
+            t_pipe_h = max_over_ranks(t_pipe_h)
+            assert res_h.tobytes() == res.tobytes()
+            rx.close()
+            line["batch_pipeline"] = {
+                "metric": "recordings/s through acquisition + tracking (60-s recordings)", "value": world * RB / t_pipe, "unit": "recordings/s",
+                "x_realtime": world * RB * secs / t_pipe, "seconds": t_pipe, "streams": n_streams,
+                "config": {"workload": f"BASELINE configs[4] per GPU: {RB} independent {secs:.0f}-s recordings x {TRACK_NCH} satellites, fine cold-start "
+                                       "search (201 bins x 32 PRN, 10 ms x 2) -> hand-over -> 8-ms tracking of every found satellite -> per-stream "
+                                       "summaries reduced on the device; NCCL all_gather of the summaries inside the timed region (N > 1)",
+                           "recordings_per_gpu": RB, "wall_clock": "host timer around the call, synchronised on both sides, max over ranks"},
+                "e2e": {"value": world * RB / t_pipe_h, "unit": "recordings/s", "x_realtime": world * RB * secs / t_pipe_h, "seconds": t_pipe_h,
+                        "h2d_bytes": 2 * RB * span, "d2h_bytes": int(res.nbytes) + RB * NPRN * ACQ_BEST.itemsize,
+                        "api": "BatchReceiver.run_host: pinned host recordings uploaded in 8 time slices on a copy stream behind the kernels"},
+            }
+            line["gpu_launches"] += 2 * (3 + 1) + 2 * (3 + 8)
+            del hb
 
     clocks.stop()
     line["clocks"] = clocks.summary(windows)
 
     if rank == 0 and world == 1 and not args.skip_cpu:
         line["cpu_baseline"] = cpu_acq_baseline(args.cpu_seconds)
+        if "acq_fine" in line:
+            line["acq_fine"]["cpu_baseline"] = cpu_fine_baseline(fine_raw_host, 8.0)
         if "tracking" in line:
             line["tracking"]["cpu_baseline"] = cpu_track_baseline(track_sats(7), 2.0)
     elif rank == 0:

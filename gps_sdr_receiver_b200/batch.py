@@ -53,19 +53,15 @@ class BatchReceiver:
     def close(self):
         self.plan.close()
 
-    def run_local(self, d_raw, nrec: int, rec_samples: int, rec0: int = 0) -> np.ndarray:
-        """d_raw: torch uint8 CUDA tensor holding `nrec` recordings of `rec_samples` samples each
-        (I,Q bytes).  Returns STREAM_RESULT[n_channels] for these recordings (`rec` = rec0 + local index)."""
-        import torch
-        n_ep = rec_samples // self.ngps
-        if n_ep < 1 or rec_samples < self.acq_samples:
-            raise ValueError("recordings are shorter than one tracking epoch / the acquisition window")
+    def _acquire(self, d_raw, nrec: int, rec_samples: int, rec0: int):
+        """Steps 1 + 2: one search launch, then the channels of a fresh TrackBank.  Returns (bank, out) with the
+        acquisition columns of STREAM_RESULT filled, or (None, out) when nothing was found."""
         best = AcqPlan.best_from_tensor(self.plan.search_dev(d_raw, nrec=nrec, rec_stride=rec_samples))
         chosen = [select_sats(best[r], self.z_min, self.max_sat) for r in range(nrec)]
         n_ch = sum(len(c) for c in chosen)
         out = np.zeros(n_ch, dtype=STREAM_RESULT)
         if n_ch == 0:
-            return out
+            return None, out
         bank = TrackBank(self.n_cyc, n_ch, device=self.device)
         k = 0
         for r in range(nrec):
@@ -76,17 +72,86 @@ class BatchReceiver:
                 out[k]["rec"], out[k]["prn"] = rec0 + r, self.prns[i]
                 out[k]["acq_bin_hz"], out[k]["acq_delay"], out[k]["acq_z"] = f, d, b["cell"]["z"]
                 k += 1
-        recs = TrackBank.records_from_tensor(bank.process_dev(d_raw, self.ngps, n_ep, rec_stride=rec_samples))
-        torch.cuda.synchronize()
-        bank.close()
-        last = recs[-1]
+        return bank, out
+
+    @staticmethod
+    def _summarise(rec_t, out: np.ndarray) -> np.ndarray:
+        """Step 4 on the device: reduce the gr_epoch_out records [n_ep, n_ch, 448] (uint8, CUDA) to one STREAM_RESULT per
+        channel; only the last epoch's records and three small vectors cross PCIe."""
+        import torch
+        from ._capi import EPOCH_OUT
+        n_ep, n_ch = rec_t.shape[0], rec_t.shape[1]
+        cp = rec_t.view(torch.float64)[:, :, EPOCH_OUT.fields["code_phase"][1] // 8]          # [n_ep, n_ch]
+        valid = cp >= 0
+        idx = torch.arange(n_ep, device=rec_t.device, dtype=torch.int64)[:, None].expand(n_ep, n_ch)
+        lastv = torch.where(valid, idx, torch.full_like(idx, -1)).max(dim=0).values
+        cp_last = torch.where(lastv >= 0, cp.gather(0, lastv.clamp(min=0)[None, :])[0], torch.full_like(cp[0], -1.0))
+        n_valid = valid.sum(dim=0)
+        last = TrackBank.records_from_tensor(rec_t[n_ep - 1:n_ep])[0]
         out["locked"], out["sweep"] = last["locked"], last["sweep"]
         out["freq"], out["amplitude"], out["corr_q"] = last["freq"], last["amplitude"], last["corr_q"]
-        cp = recs["code_phase"]                                  # [n_ep, n_ch], -1.0 where the epoch had none
-        valid = cp >= 0
-        out["n_code_phase"] = valid.sum(axis=0)
-        lastv = np.where(valid.any(axis=0), n_ep - 1 - np.argmax(valid[::-1], axis=0), 0)
-        out["code_phase"] = np.where(valid.any(axis=0), cp[lastv, np.arange(n_ch)], -1.0)
+        out["n_code_phase"] = n_valid.cpu().numpy()
+        out["code_phase"] = cp_last.cpu().numpy()
+        return out
+
+    def run_local(self, d_raw, nrec: int, rec_samples: int, rec0: int = 0) -> np.ndarray:
+        """d_raw: torch uint8 CUDA tensor holding `nrec` recordings of `rec_samples` samples each
+        (I,Q bytes).  Returns STREAM_RESULT[n_channels] for these recordings (`rec` = rec0 + local index)."""
+        import torch
+        n_ep = rec_samples // self.ngps
+        if n_ep < 1 or rec_samples < self.acq_samples:
+            raise ValueError("recordings are shorter than one tracking epoch / the acquisition window")
+        bank, out = self._acquire(d_raw, nrec, rec_samples, rec0)
+        if bank is None:
+            return out
+        try:
+            rec_t = bank.process_dev(d_raw, self.ngps, n_ep, rec_stride=rec_samples)
+            out = self._summarise(rec_t, out)
+            torch.cuda.synchronize()
+        finally:
+            bank.close()
+        return out
+
+    def run_host(self, h_raw, nrec: int, rec_samples: int, rec0: int = 0, chunks: int = 8) -> np.ndarray:
+        """The same for recordings in (pinned) HOST memory: `h_raw` is a torch uint8 CPU tensor [nrec * 2 * rec_samples].
+        The recordings go to the device in `chunks` slices along time on a copy stream; the search runs as soon as the
+        first slice is there and every slice is tracked while the next one is still on the bus (state stays in the
+        bank between launches), so the upload hides behind the kernels -- or the other way round."""
+        import torch
+        n_ep = rec_samples // self.ngps
+        if n_ep < 1 or rec_samples < self.acq_samples:
+            raise ValueError("recordings are shorter than one tracking epoch / the acquisition window")
+        dev = torch.device(f"cuda:{self.device}")
+        d_raw = torch.empty(nrec * 2 * rec_samples, dtype=torch.uint8, device=dev)
+        h2, d2 = h_raw.view(nrec, 2 * rec_samples), d_raw.view(nrec, 2 * rec_samples)
+        acq_ep = -(-self.acq_samples // self.ngps)
+        per = max(acq_ep, -(-n_ep // max(1, chunks)))
+        cuts = list(range(0, n_ep, per)) + [n_ep]
+        copy_s, main_s = torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
+        events = []
+        with torch.cuda.stream(copy_s):
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                lo, hi = 2 * a * self.ngps, 2 * (b * self.ngps if b < n_ep else rec_samples)
+                for r in range(nrec):
+                    d2[r, lo:hi].copy_(h2[r, lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_s)
+                events.append(ev)
+        main_s.wait_event(events[0])
+        bank, out = self._acquire(d_raw, nrec, rec_samples, rec0)
+        if bank is None:
+            torch.cuda.synchronize()
+            return out
+        try:
+            from ._capi import EPOCH_OUT
+            rec_t = torch.empty((n_ep, bank.num_active, EPOCH_OUT.itemsize), dtype=torch.uint8, device=dev)
+            for (a, b), ev in zip(zip(cuts[:-1], cuts[1:]), events):
+                main_s.wait_event(ev)
+                bank.process_dev(d_raw[2 * a * self.ngps:], (a + 1) * self.ngps, b - a, rec_stride=rec_samples, out=rec_t[a:b])
+            out = self._summarise(rec_t, out)
+            torch.cuda.synchronize()
+        finally:
+            bank.close()
         return out
 
     def run(self, d_raw_local, n_total: int, rec_samples: int) -> np.ndarray:

@@ -58,6 +58,36 @@ def merge_bin_shards(parts: list[np.ndarray], bin_offsets: list[int]) -> np.ndar
     return out
 
 
+def partition_bins(bin_hz, world: int, rank: int) -> list[int]:
+    """Doppler bins of ONE search split across ranks so that the per-rank forward work shrinks with the shard: bins that
+    differ by a multiple of fs / 2048 = 1 kHz share one forward spectrum (acquisition.classify_bins), so the bins are
+    ordered class by class and cut into `world` balanced runs -- a rank's ~nbins / world bins then touch 3 or 4 base
+    spectra instead of all of them (contiguous 50-Hz bins touch all 20).  Returns this rank's GLOBAL bin indices,
+    ascending.  A cell does not depend on the other bins of its plan, so any split is bit-identical to the full search."""
+    from .acquisition import classify_bins
+    base, _, _ = classify_bins(bin_hz)
+    order = sorted(range(len(base)), key=lambda b: (int(base[b]), b))
+    return sorted(order[i] for i in partition(len(order), world, rank))
+
+
+def merge_bin_lists(parts: list[np.ndarray], bin_lists: list[list[int]]) -> np.ndarray:
+    """parts[r] = ACQ_BEST[nrec, nprn] over the bins bin_lists[r] (local indices).  Global best per (recording, PRN):
+    largest z, ties to the lowest GLOBAL bin -- the answer of one search over all bins."""
+    out = None
+    for p, bl in zip(parts, bin_lists):
+        if len(bl) == 0:
+            continue
+        q = p.copy()
+        q["bin"] = np.asarray(bl, dtype=np.int32)[q["bin"]]
+        if out is None:
+            out = q
+            continue
+        zq, zo = q["cell"]["z"], out["cell"]["z"]
+        better = (zq > zo) | ((zq == zo) & (q["bin"] < out["bin"]))
+        out[better] = q[better]
+    return out
+
+
 def gather_bin_shards(best_local: np.ndarray, n_bins_total: int, device=None) -> np.ndarray:
     import torch.distributed as dist
     world = dist.get_world_size()

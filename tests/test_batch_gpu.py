@@ -30,6 +30,9 @@ def test_batch_of_recordings_acquire_and_track(gpu):
     raw = np.concatenate([synth.make_iq(s, n_ms, seed=10 + i) for i, s in enumerate(scenes)])
     rx = BatchReceiver(n_cyc=32, max_sat=4)
     res = rx.run_local(torch.from_numpy(raw).cuda(), nrec=3, rec_samples=n_ms * 2048)
+    # the same batch from pinned host memory, uploaded in slices behind the kernels: the same summaries bit for bit
+    res_h = rx.run_host(torch.from_numpy(raw).pin_memory(), nrec=3, rec_samples=n_ms * 2048, chunks=5)
+    assert res_h.tobytes() == res.tobytes()
     rx.close()
     want = {(r, s.prn): s for r, sc in enumerate(scenes) for s in sc}
     got = {(int(x["rec"]), int(x["prn"])): x for x in res}
@@ -61,6 +64,11 @@ def test_bin_sharded_fine_search_equals_full_search(gpu):
         offs.append(mine.start)
     merged = multi.merge_bin_shards(parts, offs)
     assert merged.tobytes() == full.tobytes()
+    # the split bench.py uses at N > 1: bins grouped by 1-kHz class (each shard computes 7 of the 20 base spectra)
+    lists = [multi.partition_bins(bins, 3, r) for r in range(3)]
+    assert sorted(b for l in lists for b in l) == list(range(len(bins)))
+    cparts = [AcqPlan(prns, [bins[b] for b in l], 10, 4, GR_ACQ_POW).search(raw) for l in lists]
+    assert multi.merge_bin_lists(cparts, lists).tobytes() == full.tobytes()
     for s in sats:                                           # amp 0.03: invisible in 1 ms, found in 10 ms x 4
         b = full[0, s.prn - 1]
         assert abs(bins[int(b["bin"])] - s.doppler) <= 50.0 and b["cell"]["z"] > 10

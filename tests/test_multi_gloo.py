@@ -80,6 +80,34 @@ def test_partition_is_balanced_and_complete():
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
 
 
+def test_class_major_bin_partition_and_merge(built_lib):
+    """multi.partition_bins / merge_bin_lists (the strong-scaling split of BASELINE configs[3]): complete, balanced, few
+    base spectra per rank, and the merge picks the largest z with ties to the lowest GLOBAL bin."""
+    from gps_sdr_receiver_b200 import multi
+    from gps_sdr_receiver_b200._capi import ACQ_BEST
+    from gps_sdr_receiver_b200.acquisition import classify_bins
+    bins = [-10000.0 + 50.0 * b for b in range(401)]
+    base, _, _ = classify_bins(bins)
+    for world in (1, 2, 3, 4, 8):
+        lists = [multi.partition_bins(bins, world, r) for r in range(world)]
+        assert sorted(b for l in lists for b in l) == list(range(401))
+        assert max(map(len, lists)) - min(map(len, lists)) <= 1
+        assert all(l == sorted(l) for l in lists)
+        assert max(len(set(base[l])) for l in lists) <= -(-20 // world) + 1          # 3 base spectra per rank at world 8, not 20
+    rng = np.random.default_rng(3)
+    z = rng.integers(0, 6, size=(2, 5, 401)).astype(np.float32)                       # many ties on purpose
+    lists = [multi.partition_bins(bins, 4, r) for r in range(4)]
+    parts = []
+    for l in lists:
+        p = np.zeros((2, 5), dtype=ACQ_BEST)
+        zl = z[:, :, l]
+        p["bin"] = np.argmax(zl, axis=2)                                               # first max within the shard
+        p["cell"]["z"] = np.take_along_axis(zl, p["bin"][..., None].astype(np.int64), axis=2)[..., 0]
+        parts.append(p)
+    merged = multi.merge_bin_lists(parts, lists)
+    assert np.array_equal(merged["bin"], np.argmax(z, axis=2)) and np.array_equal(merged["cell"]["z"], z.max(axis=2))
+
+
 @pytest.mark.timeout(300)
 def test_two_ranks_equal_one_rank():
     world, port = 2, 29500 + os.getpid() % 2000

@@ -23,6 +23,40 @@ def _circ(a, b):
     return np.abs(d)
 
 
+# Measured maxima are collected per fixture, written to gpurun_out/track_parity_measured.json when that directory exists,
+# and asserted against PINS: the bound north_star states (1e-4) wherever it holds, else 1.5 x the maximum measured on the
+# B200 for the committed kernel (so a regression of that size fails).  Where a quantity cannot reach 1e-4 the reason is
+# the reference's own float32 phase-argument noise, not the kernel: oracle/parity_floor.py runs the oracle against
+# itself with a mathematically exact NCO and finds FREQ bit-equal on only half the epochs (up to 11 ulp), PHASE 8.5e-5
+# rad, AMPLITUDE / STD_DEV 1.5e-5 and complex prompts 3.7e-4 apart (profiles/parity_floor_r02.txt).
+MEASURED = {}
+PINS = {
+    # quantity: (bound, meaning)
+    "code_phase_abs": 2e-4,        # samples (0.03 m; north_star: pseudorange 0.1 m = 6.8e-4 sample)
+    "max_corr_rel": 1e-4,
+    "freq_rel": 1e-6,              # FREQ, relative (+ 1e-3 Hz absolute): 100 x tighter than north_star's 1e-4
+    "phase_abs": 1e-3,             # rad, circular
+    "amp_rel": 2e-4,
+    "std_rel": 2e-4,
+    "prompt_abs_rel": 1e-4,        # | |prompt| - |ref| | / max |ref|
+    "prompt_cplx_rel": 1e-3,       # | prompt - ref | / max |ref|
+}
+
+
+def _note(tag, name, value):
+    MEASURED.setdefault(tag, {})
+    MEASURED[tag][name] = max(float(value), MEASURED[tag].get(name, 0.0))
+
+
+def _dump_measured():
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "track_parity_measured.json"), "w") as f:
+            json.dump(MEASURED, f, indent=1, sort_keys=True)
+
+
 def _compare_channel(rows_g, recs, prompts_g, plen_g, edges_g, edges_got, tag, exact_edges=True):
     g = lambda name: rows_g[:, COL[name]]
     for name, field in (("sweep", "sweep"), ("DELAY", "delay"), ("LOCKED", "locked"), ("MS_TIME", "ms_time"),
@@ -31,30 +65,32 @@ def _compare_channel(rows_g, recs, prompts_g, plen_g, edges_g, edges_got, tag, e
     assert np.array_equal(recs["corr_q"], g("corrQ")) and np.array_equal(recs["corr_l"], g("corrL")), tag
     has_cp = g("codePhase") >= 0
     assert np.array_equal(recs["code_phase"] >= 0, has_cp), tag
-    assert np.abs(recs["code_phase"][has_cp] - g("codePhase")[has_cp]).max() < 2e-4, tag      # samples (0.03 m)
-    np.testing.assert_allclose(recs["max_corr"], g("MAX_CORR"), rtol=1e-4, err_msg=tag)
-    np.testing.assert_allclose(recs["freq"], g("FREQ"), rtol=1e-6, atol=1e-3, err_msg=tag)
-    assert _circ(recs["phase"], g("PHASE")).max() < 1e-3, tag
+    _note(tag, "code_phase_abs", np.abs(recs["code_phase"][has_cp] - g("codePhase")[has_cp]).max())
+    _note(tag, "max_corr_rel", np.abs(recs["max_corr"] / g("MAX_CORR") - 1).max())
+    fg, fr = g("FREQ").astype(np.float32), recs["freq"].astype(np.float32)
+    ulp = np.abs(fg.view(np.int32).astype(np.int64) - fr.view(np.int32).astype(np.int64))
+    same_sign = np.sign(fg) == np.sign(fr)
+    _note(tag, "freq_max_ulp", ulp[same_sign].max())
+    MEASURED[tag]["freq_biteq_frac"] = float((ulp == 0).mean())
+    _note(tag, "freq_rel", (np.maximum(np.abs(recs["freq"] - g("FREQ")) - 1e-3, 0) / np.abs(g("FREQ"))).max())
+    _note(tag, "phase_abs", _circ(recs["phase"], g("PHASE")).max())
     tr = g("tracked") > 0
-    np.testing.assert_allclose(recs["amplitude"][tr], g("AMPLITUDE")[tr], rtol=2e-4, err_msg=tag)
-    np.testing.assert_allclose(recs["std_dev"][tr], g("STD_DEV")[tr], rtol=2e-4, err_msg=tag)
+    _note(tag, "amp_rel", np.abs(recs["amplitude"][tr] / g("AMPLITUDE")[tr] - 1).max())
+    _note(tag, "std_rel", np.abs(recs["std_dev"][tr] / g("STD_DEV")[tr] - 1).max())
     rep = g("report") > 0
     assert np.array_equal(recs["rep_sweep"][rep].astype(np.float64), g("SWP")[rep]), tag
     assert np.array_equal(recs["n_prompt"][tr], plen_g[tr]), tag
-    # Prompt values.  |prompt| within 1e-4.  The complex value additionally carries the carrier
-    # phase, and the reference keeps FREQ in float32: the kernel's FREQ agrees to the last bit or
-    # a few ulp (1 ulp = 2.4e-4 Hz at 3 kHz; up to 7 ulp = 5.7e-7 relative right after a re-sweep,
-    # where the unlocked loop gain of 10 amplifies 1e-6-level discriminator differences), and
-    # 1.7e-3 Hz rotates the last prompt of a 32-ms epoch by 2*pi*1.7e-3*0.032 = 3.4e-4 rad until
-    # the loop pulls it back (trace: tools/diag_track.py).  Hence 1e-3 of the amplitude for the
-    # complex difference; FREQ itself is checked at 1e-6 relative below.
+    # Prompt values: |prompt| and the complex value (which additionally carries the carrier phase, i.e. FREQ's ulps).
     for r in np.nonzero(tr)[0]:
         n = int(plen_g[r])
         got = np.ascontiguousarray(recs["prompt"][r][:2 * n]).view(np.complex64)
         ref = prompts_g[r][:n]
         scale = np.abs(ref).max()
-        assert np.abs(np.abs(got) - np.abs(ref)).max() < 1e-4 * scale + 1e-7, (tag, r)
-        assert np.abs(got - ref).max() < 1e-3 * scale + 1e-7, (tag, r)
+        _note(tag, "prompt_abs_rel", np.abs(np.abs(got) - np.abs(ref)).max() / scale)
+        _note(tag, "prompt_cplx_rel", np.abs(got - ref).max() / scale)
+    _dump_measured()
+    for name, bound in PINS.items():
+        assert MEASURED[tag][name] <= bound, (tag, name, MEASURED[tag][name], bound)
     got_e = set(map(tuple, np.array(edges_got, dtype=np.int64).reshape(-1, 3).tolist()))
     ref_e = set(map(tuple, edges_g.tolist()))
     if exact_edges:
@@ -272,3 +308,40 @@ def test_dense_form_equals_standard_form_bit_for_bit(gpu, monkeypatch):
     monkeypatch.delenv("GPSB200_TRACK_DENSE")
     assert out["0"].tobytes() == out["1"].tobytes()
     assert out["1"]["locked"][-1].all()
+
+
+def test_corrlst_fifo_past_60_s_at_ncyc8_and_quality_triggered_sweep(gpu):
+    """N_CYC = 8 is the one stream length where CORRLST's capacity (60 * NO_SEC = 7680 entries, gpslib.py:1082-1083) equals
+    the kernel's ring size: past 60 s every append evicts the oldest entry (gpslib.py:1331-1339).  A satellite that
+    disappears after 8 s: CORR_Q must keep falling as the good entries leave the list, and checkCorrQuality
+    (gpslib.py:1134-1138) must start the re-sweep at the same epoch as the oracle (with a frozen sum it never would)."""
+    import torch
+    from gps_sdr_receiver_b200 import synth
+    from gps_sdr_receiver_b200.tracking import TrackBank
+    n_cyc, ngps = 8, 8 * 2048
+    n_sig, n_ep = 1000, 8400
+    sat = synth.Sat(prn=13, doppler=1510.0, delay=700.4, amp=0.08, bit_offset_ms=5, bit_seed=3)
+    raw = torch.empty(2 * n_ep * ngps, dtype=torch.uint8, device="cuda")
+    synth.make_iq_dev([sat], n_sig * n_cyc, seed=31, out=raw[:2 * n_sig * ngps])
+    piece = 2000
+    for e0 in range(n_sig, n_ep, piece):                      # noise only from here on
+        e1 = min(n_ep, e0 + piece)
+        synth.make_iq_dev([], (e1 - e0) * n_cyc, seed=31, start_sample=e0 * ngps, out=raw[2 * e0 * ngps:2 * e1 * ngps])
+    bank = TrackBank(n_cyc, 2)
+    bank.add(13, 1500.0, 701)
+    recs = TrackBank.records_from_tensor(bank.process_dev(raw, ngps, n_ep))[:, 0]
+    torch.cuda.synchronize()
+    bank.close()
+    host = raw.cpu().numpy()
+    ch = orc.Channel(13, 1500.0, delay=701, n_cyc=n_cyc)
+    cq, cl, sw = np.empty(n_ep), np.empty(n_ep), np.zeros(n_ep, dtype=bool)
+    for e in range(n_ep):
+        s, _, _, (q, l) = ch.process(orc.raw_to_complex(host[2 * e * ngps:2 * (e + 1) * ngps]), np.int64((e + 1) * ngps))
+        cq[e], cl[e], sw[e] = q, l, s
+    assert cq[7600] > -0.9 and cq[n_ep - 1] != cq[7700]            # the scenario does what it is meant to
+    first = int(np.argmax(recs["erased"] & 2 != 0))                 # epoch whose report started the re-sweep
+    assert (recs["erased"] & 2 != 0).any() and first > 7680, first
+    assert np.array_equal(recs["corr_q"], cq), np.nonzero(recs["corr_q"] != cq)[0][:5]
+    assert np.array_equal(recs["corr_l"], cl)
+    assert np.array_equal(recs["sweep"].astype(bool), sw), np.nonzero(recs["sweep"].astype(bool) != sw)[0][:5]
+    assert sw[first + 1] or recs["tracked"][first + 1] == 0
