@@ -37,6 +37,7 @@
 #include <vector>
 
 #include "gr_fft2048.cuh"
+#include "gr_cpk.cuh"
 #include "gr_internal.h"
 
 #define GR_DF_CAP 128            // NO_SEC = 1024 // N_CYC <= 128  (N_CYC >= 8)
@@ -119,6 +120,10 @@ struct TrackSmem {
     float4 red[GR_MAX_NCYC + 2];         // reduced prompt rows: (S_k, B_k)
     float4 xs[GR_MAX_NCYC + 2];          // (X_k, XB_k): affine-corrected, block-rotated
     float qred[4][6];                    // per-warp sums of q: all rows, masked row 0, wrapped rows
+    cf sigma[8];                         // vector form: exp(-i w i / fs), i = 0..7
+    cf qb[8];                            // vector form: the replica values of the samples between the window start 8 (d >> 3) and d
+    cf qbsum;
+    int dq;                              // vector form: chunk rotation of the fold pass = DELAY >> 3 at the start of the epoch
     double sh_d[8];
     float sh_f[8];
     int sh_i[8];
@@ -171,7 +176,7 @@ __device__ __forceinline__ cf expmi(float a) {   // exp(-i a)
     return cf{c, -s};
 }
 __device__ __forceinline__ cf expmi_d(double a) {   // exp(-i a), argument reduced in double
-    a -= GR_TWO_PI_D * rint(a / GR_TWO_PI_D);
+    a -= GR_TWO_PI_D * rint(a * (1.0 / GR_TWO_PI_D));      // no FP64 division on the epoch's critical path
     return expmi((float)a);
 }
 
@@ -292,9 +297,84 @@ __device__ __forceinline__ void fold_blocks(cf* F, const void* src, int first, i
     }
 }
 
+// ---- vector form of the two sample passes (staged uint8 I/Q) ---------------------------------------------------------
+// The staged block is read 16 bytes (8 samples) at a time: a 2048-sample block is 256 chunks, thread t owns the chunks
+// u0 = (t + dq) & 255 and u1 = u0 ^ 128 of EVERY block (dq = DELAY >> 3 puts the code-period boundary into thread 0's
+// first chunk).  Arithmetic on the packed FP32 instructions (gr_cpk.cuh): a sample costs two PRMT + one FADD2 (bytes ->
+// integer-valued floats) and two FFMA2 (complex multiply-accumulate), against one LDS.U16, two PRMT, two FADD, four FFMA
+// and address / select work in the scalar form (ncu, profiles/track_r01_v5_regions.txt: 115 IADD3 + 100 FSEL + 96 PRMT per
+// 126 FFMA in the prompt pass).
+__device__ __forceinline__ cpk cpk_bc(float v) { return cpk_make(v, v); }
+__device__ __forceinline__ void load8_u8(const unsigned char* p, cpk* x) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const cpk magic = cpk_make(-8388608.0f, -8388608.0f);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        x[2 * k] = cpk_add(cpk_make(__uint_as_float(__byte_perm(w[k], 0x4B000000u, 0x7540)),
+                                    __uint_as_float(__byte_perm(w[k], 0x4B000000u, 0x7541))), magic);
+        x[2 * k + 1] = cpk_add(cpk_make(__uint_as_float(__byte_perm(w[k], 0x4B000000u, 0x7542)),
+                                        __uint_as_float(__byte_perm(w[k], 0x4B000000u, 0x7543))), magic);
+    }
+}
+// A[8 h + i] = sum_b R_b x_b[8 u_h + i]  (bytes as integers; the affine map is applied to the sum), rsum = sum_b R_b
+__device__ __forceinline__ void fold_blocks_vec(cpk* A, cf& rsum, const unsigned char* stage, int first, int nblk, int u0, int u1,
+                                                const cf* Rm) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) A[i] = cpk_make(0.f, 0.f);
+    rsum = cf{0.f, 0.f};
+    for (int b = first; b < first + nblk; ++b) {
+        const cf R = Rm[b + 1];
+        rsum = cadd(rsum, R);
+        const cpk Rp = cpk_make(R.x, R.y), Rs = cpk_make(-R.y, R.x);      // x R = xr (Rr, Ri) + xi (-Ri, Rr)
+        const unsigned char* pb = stage + (size_t)b * (GR_N * 2);
+        cpk x[8], y[8];
+        load8_u8(pb + 16 * u0, x);
+        load8_u8(pb + 16 * u1, y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float xr, xi, yr, yi;
+            cpk_split(x[i], xr, xi);
+            cpk_split(y[i], yr, yi);
+            A[i] = cpk_fma(cpk_bc(xr), Rp, A[i]);
+            A[8 + i] = cpk_fma(cpk_bc(yr), Rp, A[8 + i]);
+            A[i] = cpk_fma(cpk_bc(xi), Rs, A[i]);
+            A[8 + i] = cpk_fma(cpk_bc(yi), Rs, A[8 + i]);
+        }
+    }
+}
+// Exchange "thread owns chunks" -> "thread t owns elements t + 128 j" (the FFT's input layout) through 16 KiB of shared
+// memory: chunk u = 64 bytes, its four 16-byte quarters swizzled by (u >> 1) & 3 so that the 128-bit stores of a
+// quarter-warp and the 64-bit loads of a half-warp are conflict-free (checked exhaustively on the host, all rotations).
+__device__ __forceinline__ void aex_write(float4* ex, int u, const cf* F8) {
+    const int sw = (u >> 1) & 3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ex[4 * u + (c ^ sw)] = make_float4(F8[2 * c].x, F8[2 * c].y, F8[2 * c + 1].x, F8[2 * c + 1].y);
+}
+__device__ __forceinline__ void aex_read(const float4* ex, int t, cf* F) {
+    const float2* e2 = reinterpret_cast<const float2*>(ex);
+    const int i = t & 7;
+    const int off = 8 * (t >> 3) + 2 * ((i >> 1) ^ ((t >> 4) & 3)) + (i & 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { const float2 v = e2[off + 128 * j]; F[j] = cf{v.x, v.y}; }
+}
+// r of the first sample of chunk u: the reference's float32 argument fl32(phase + fl32(w * fl32((8 u + 1) / fs)))
+__device__ __forceinline__ cf chunk_rot(float w32, float phase32, int u) {
+    const float tsec = __fdiv_rn((float)(8 * u + 1), GR_FS);
+    return expmi(__fadd_rn(phase32, __fmul_rn(w32, tsec)));
+}
+// NCO tables of the vector form: sigma_i, R_{k-1}.  Caller syncs.
+__device__ __forceinline__ void nco_setup_vec(float w32, int n_cyc, int t, TrackSmem* S) {
+    if (t < 8) S->sigma[t] = expmi_d((double)w32 * (double)t * (1.0 / (double)GR_FS));
+    if (t >= 32 && t < 32 + n_cyc + 1) {
+        const int k = t - 32;
+        S->Rm[k] = expmi_d((double)w32 * (double)(k - 1) * 1e-3);
+    }
+}
+
 // NCO tables of one wipe-off: rho_j, R_{k-1}; returns this thread's r_t.  Caller syncs.
 __device__ __forceinline__ cf nco_setup(float w32, float phase32, int n_cyc, int t, TrackSmem* S) {
-    if (t < 16) S->rho[t] = expmi_d((double)w32 * (double)(128 * t) / (double)GR_FS);
+    if (t < 16) S->rho[t] = expmi_d((double)w32 * (double)(128 * t) * (1.0 / (double)GR_FS));
     if (t >= 32 && t < 32 + n_cyc + 1) {
         const int k = t - 32;
         S->Rm[k] = expmi_d((double)w32 * (double)(k - 1) * 1e-3);
@@ -391,6 +471,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
     TrackSmem* S = reinterpret_cast<TrackSmem*>(smem_raw + a.buf_bytes);
     unsigned char* stage = smem_raw + a.buf_bytes + ((sizeof(TrackSmem) + 15) & ~(size_t)15);
     GrChanHot* C = &S->CH.h;
+    constexpr bool kVec = (IN_FMT == GR_IN_U8IQ) && kStage;      // vector form of the sample passes (staged uint8 I/Q)
 
     const int t = threadIdx.x;
     const int slot = a.slots[blockIdx.x];
@@ -447,6 +528,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
             if (req) { st_init_sweep(C, G, a.cfg); erased = 1; }
             O->erased = erased;
             S->branch_sweep = C->sweep;
+            S->dq = C->delay >> 3;
             S->w32 = weak_w32(C->freq, C->freq_weak);
             S->phase32 = C->phase;
             O->edge_mask = 0ull;
@@ -518,9 +600,40 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
         } else {
             // =============== tracking branch (gpslib.py:1175-1208) ===============
             const float w32 = S->w32, phase32 = S->phase32;
-            const cf rt = nco_setup(w32, phase32, n_cyc, t, S);
-            __syncthreads();
-            {
+            cf rt = cf{0.f, 0.f};
+            int dq = 0, u0 = 0, u1 = 0;
+            cf E0 = cf{0.f, 0.f}, E1 = cf{0.f, 0.f};
+            if constexpr (kVec) {
+                nco_setup_vec(w32, n_cyc, t, S);
+                dq = S->dq;
+                u0 = (t + dq) & 255;
+                u1 = u0 ^ 128;
+                E0 = chunk_rot(w32, phase32, u0);
+                E1 = chunk_rot(w32, phase32, u1);
+                __syncthreads();
+                cf F[16];
+                {
+                    cpk A[16];
+                    cf rsum;
+                    fold_blocks_vec(A, rsum, stage, (n_cyc - corr_avg) / 2, corr_avg, u0, u1, S->Rm);
+                    cf G[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float ar, ai;
+                        cpk_split(A[i], ar, ai);
+                        const cf r = cmul(i < 8 ? E0 : E1, S->sigma[i & 7]);
+                        G[i] = cmul(affine_sum<IN_FMT>(cf{ar, ai}, rsum), r);
+                    }
+                    float4* ex = reinterpret_cast<float4*>(kDense ? fftbuf : fftbuf + GR_B1_ELEMS);   // free at this point (see fft2048)
+                    aex_write(ex, u0, G);
+                    aex_write(ex, u1, G + 8);
+                    __syncthreads();
+                    aex_read(ex, t, F);
+                }
+                corr_and_stats<kDense>(F, cs, 1.0f / ((float)corr_avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
+            } else {
+                rt = nco_setup(w32, phase32, n_cyc, t, S);
+                __syncthreads();
                 cf F[16];
                 fold_blocks<IN_FMT, kStage>(F, src, (n_cyc - corr_avg) / 2, corr_avg, rt, t, S);
                 corr_and_stats<kDense>(F, cs, 1.0f / ((float)corr_avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
@@ -540,77 +653,187 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
             }
             __syncthreads();
 
-            // ---- prompt integrate & dump (decodeData) in row-rotated layout ----
+            // ---- prompt integrate & dump (decodeData) ----
             const int d = S->delay;
-            const int jb = d >> 7, dlow = d & 127;
-            const bool inB = t < dlow;                       // row 0, before the code-period boundary
-            cf q[16];
-            {
-                cf qall = cf{0.f, 0.f}, qw = cf{0.f, 0.f};
-                const cf R1 = S->Rm[2];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int row = (j + jb) & 15;
-                    const bool wrapped = (j + jb) >= 16;
-                    const int i = t + 128 * row;
-                    const float c = S->code[(i - d) & (GR_N - 1)];
-                    cf r = cmul(rt, S->rho[row]);
-                    if (wrapped) r = cmul(r, R1);
-                    q[j] = cf{r.x * c, r.y * c};
-                    qall = cadd(qall, q[j]);
-                    if (wrapped) qw = cadd(qw, q[j]);
+            if constexpr (kVec) {
+                // Vector form: pass k sums the 2048 samples from 8 (d >> 3) + 2048 (k - 1) on, thread t its chunks u0, u1
+                // (a chunk whose index ran past 255 lies in the next block: "wrapped").  The code-period boundary d sits
+                // inside thread 0's first chunk: the d & 7 samples in front of it (B_k) are summed once more by thread k
+                // after the passes, and the true 1-ms sums are S_k - B_k + B_{k+1} as in the scalar form.
+                const int r8 = d & 7;
+                if ((d >> 3) != dq) {                                   // DELAY moved to another chunk (rare; uniform)
+                    dq = d >> 3;
+                    u0 = (t + dq) & 255;
+                    u1 = u0 ^ 128;
+                    E0 = chunk_rot(w32, phase32, u0);
+                    E1 = chunk_rot(w32, phase32, u1);
                 }
-                float v[6] = {qall.x, qall.y, inB ? q[0].x : 0.f, inB ? q[0].y : 0.f, qw.x, qw.y};
+                const bool wr0 = t + dq >= 256, wr1 = t + dq + 128 >= 256;
+                float qr[16], qi[16];
+                {
+                    cf qall = cf{0.f, 0.f}, qw = cf{0.f, 0.f}, qbs = cf{0.f, 0.f};
+                    const cf R1 = S->Rm[2];
 #pragma unroll
-                for (int m = 0; m < 6; ++m) {
-                    v[m] = warp_sum(v[m]);
-                    if ((t & 31) == 0) S->qred[t >> 5][m] = v[m];
-                }
-            }
-            for (int k0 = 0; k0 <= n_cyc; k0 += a.part_rows) {
-                const int k1 = (k0 + a.part_rows <= n_cyc + 1) ? k0 + a.part_rows : n_cyc + 1;
-                for (int k = k0; k < k1; ++k) {
-                    const long long base = (long long)128 * jb + (long long)GR_N * (k - 1) + t;
-                    // rows outside the epoch (pass 0: not yet wrapped, last pass: wrapped) read a clamped
-                    // address and are zeroed with selects: no branches around the loads
-                    const int vmode = (k == 0) ? 1 : (k == n_cyc ? 2 : 0);
-                    cf x[16];
+                    for (int h = 0; h < 2; ++h) {
+                        const int uh = h ? u1 : u0;
+                        const bool wr = h ? wr1 : wr0;
+                        cf Eh = h ? E1 : E0;
+                        if (wr) Eh = cmul(Eh, R1);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const bool wrapped = (j + jb) >= 16;
-                        const bool valid = vmode == 0 || (vmode == 1 ? wrapped : !wrapped);
-                        const long long n = valid ? base + 128 * j : (long long)t;
-                        const cf v = load_raw<IN_FMT, kStage>(src, n);
-                        x[j].x = valid ? v.x : 0.f;
-                        x[j].y = valid ? v.y : 0.f;
-                    }
-                    cf p0 = cmul(x[0], q[0]);
-                    cf acc = p0;
-#pragma unroll
-                    for (int j = 1; j < 16; ++j) {
-                        acc.x = fmaf(x[j].x, q[j].x, acc.x);
-                        acc.x = fmaf(-x[j].y, q[j].y, acc.x);
-                        acc.y = fmaf(x[j].x, q[j].y, acc.y);
-                        acc.y = fmaf(x[j].y, q[j].x, acc.y);
-                    }
-                    if (!inB) p0 = cf{0.f, 0.f};
-                    part[(k - k0) * 128 + t] = make_float4(acc.x, acc.y, p0.x, p0.y);
-                }
-                __syncthreads();
-                {   // reduce the staged rows: warp w takes rows w, w+4, ...
-                    const int w = t >> 5, l = t & 31;
-                    for (int r = w; r < k1 - k0; r += 4) {
-                        float4 v = part[r * 128 + l];
-#pragma unroll
-                        for (int m = 1; m < 4; ++m) {
-                            const float4 u = part[r * 128 + l + 32 * m];
-                            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+                        for (int i = 0; i < 8; ++i) {
+                            const float c = S->code[(8 * uh + i - d) & (GR_N - 1)];
+                            const cf r = cmul(Eh, S->sigma[i]);
+                            const cf q = cf{r.x * c, r.y * c};
+                            qr[8 * h + i] = q.x;
+                            qi[8 * h + i] = q.y;
+                            qall = cadd(qall, q);
+                            if (wr) qw = cadd(qw, q);
+                            if (h == 0 && t == 0) {                     // thread 0's first chunk starts at 8 dq <= d: never wrapped
+                                const cf qm = i < r8 ? q : cf{0.f, 0.f};
+                                S->qb[i] = qm;
+                                qbs = cadd(qbs, qm);
+                            }
                         }
-                        v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
-                        if (l == 0) S->red[k0 + r] = v;
+                    }
+                    float v[6] = {qall.x, qall.y, qbs.x, qbs.y, qw.x, qw.y};
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) {
+                        v[m] = warp_sum(v[m]);
+                        if ((t & 31) == 0) S->qred[t >> 5][m] = v[m];
                     }
                 }
-                __syncthreads();
+                float2* part2 = reinterpret_cast<float2*>(smem_raw);
+                const int rows_cap = a.buf_bytes / (128 * 8);
+                const int part_rows = rows_cap < n_cyc + 1 ? rows_cap : n_cyc + 1;
+                const unsigned char* p0 = stage + 16 * u0;
+                const unsigned char* p1 = stage + 16 * u1;
+                for (int k0 = 0; k0 <= n_cyc; k0 += part_rows) {
+                    const int k1 = (k0 + part_rows <= n_cyc + 1) ? k0 + part_rows : n_cyc + 1;
+                    for (int k = k0; k < k1; ++k) {
+                        const int b0 = k - 1 + (wr0 ? 1 : 0), b1 = k - 1 + (wr1 ? 1 : 0);
+                        const bool v0 = (unsigned)b0 < (unsigned)n_cyc, v1 = (unsigned)b1 < (unsigned)n_cyc;
+                        cpk x[8], y[8];
+                        load8_u8(p0 + (size_t)(v0 ? b0 : 0) * (GR_N * 2), x);
+                        load8_u8(p1 + (size_t)(v1 ? b1 : 0) * (GR_N * 2), y);
+                        // x q = (xr qr - xi qi) + i (xr qi + xi qr): a1 = sum (xr, xi) qr, a2 = sum (xr, xi) qi
+                        cpk a1 = cpk_make(0.f, 0.f), a2 = a1, c1 = a1, c2 = a1;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            a1 = cpk_fma(x[i], cpk_bc(qr[i]), a1);
+                            c1 = cpk_fma(y[i], cpk_bc(qr[8 + i]), c1);
+                            a2 = cpk_fma(x[i], cpk_bc(qi[i]), a2);
+                            c2 = cpk_fma(y[i], cpk_bc(qi[8 + i]), c2);
+                        }
+                        float a1l, a1h, a2l, a2h, c1l, c1h, c2l, c2h;
+                        cpk_split(a1, a1l, a1h); cpk_split(a2, a2l, a2h); cpk_split(c1, c1l, c1h); cpk_split(c2, c2l, c2h);
+                        const float re = (v0 ? a1l - a2h : 0.f) + (v1 ? c1l - c2h : 0.f);
+                        const float im = (v0 ? a2l + a1h : 0.f) + (v1 ? c2l + c1h : 0.f);
+                        part2[(k - k0) * 128 + t] = make_float2(re, im);
+                    }
+                    __syncthreads();
+                    if (k0 == 0 && t <= n_cyc) {                          // B_k: the d & 7 samples in front of the boundary, pass k = t
+                        cf bsum = cf{0.f, 0.f};
+                        if (t >= 1) {
+                            cpk x[8];
+                            load8_u8(stage + (size_t)(t - 1) * (GR_N * 2) + 16 * dq, x);
+#pragma unroll
+                            for (int i = 0; i < 7; ++i) {
+                                float xr, xi;
+                                cpk_split(x[i], xr, xi);
+                                const cf qm = S->qb[i];
+                                bsum.x = fmaf(xr, qm.x, bsum.x); bsum.x = fmaf(-xi, qm.y, bsum.x);
+                                bsum.y = fmaf(xr, qm.y, bsum.y); bsum.y = fmaf(xi, qm.x, bsum.y);
+                            }
+                        }
+                        S->red[t].z = bsum.x;
+                        S->red[t].w = bsum.y;
+                    }
+                    {   // reduce the staged rows: warp w takes rows w, w+4, ...
+                        const int w = t >> 5, l = t & 31;
+                        for (int r = w; r < k1 - k0; r += 4) {
+                            float2 v = part2[r * 128 + l];
+#pragma unroll
+                            for (int m = 1; m < 4; ++m) {
+                                const float2 u = part2[r * 128 + l + 32 * m];
+                                v.x += u.x; v.y += u.y;
+                            }
+                            v.x = warp_sum(v.x); v.y = warp_sum(v.y);
+                            if (l == 0) { S->red[k0 + r].x = v.x; S->red[k0 + r].y = v.y; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            } else {
+                const int jb = d >> 7, dlow = d & 127;
+                const bool inB = t < dlow;                       // row 0, before the code-period boundary
+                cf q[16];
+                {
+                    cf qall = cf{0.f, 0.f}, qw = cf{0.f, 0.f};
+                    const cf R1 = S->Rm[2];
+    #pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int row = (j + jb) & 15;
+                        const bool wrapped = (j + jb) >= 16;
+                        const int i = t + 128 * row;
+                        const float c = S->code[(i - d) & (GR_N - 1)];
+                        cf r = cmul(rt, S->rho[row]);
+                        if (wrapped) r = cmul(r, R1);
+                        q[j] = cf{r.x * c, r.y * c};
+                        qall = cadd(qall, q[j]);
+                        if (wrapped) qw = cadd(qw, q[j]);
+                    }
+                    float v[6] = {qall.x, qall.y, inB ? q[0].x : 0.f, inB ? q[0].y : 0.f, qw.x, qw.y};
+    #pragma unroll
+                    for (int m = 0; m < 6; ++m) {
+                        v[m] = warp_sum(v[m]);
+                        if ((t & 31) == 0) S->qred[t >> 5][m] = v[m];
+                    }
+                }
+                for (int k0 = 0; k0 <= n_cyc; k0 += a.part_rows) {
+                    const int k1 = (k0 + a.part_rows <= n_cyc + 1) ? k0 + a.part_rows : n_cyc + 1;
+                    for (int k = k0; k < k1; ++k) {
+                        const long long base = (long long)128 * jb + (long long)GR_N * (k - 1) + t;
+                        // rows outside the epoch (pass 0: not yet wrapped, last pass: wrapped) read a clamped
+                        // address and are zeroed with selects: no branches around the loads
+                        const int vmode = (k == 0) ? 1 : (k == n_cyc ? 2 : 0);
+                        cf x[16];
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const bool wrapped = (j + jb) >= 16;
+                            const bool valid = vmode == 0 || (vmode == 1 ? wrapped : !wrapped);
+                            const long long n = valid ? base + 128 * j : (long long)t;
+                            const cf v = load_raw<IN_FMT, kStage>(src, n);
+                            x[j].x = valid ? v.x : 0.f;
+                            x[j].y = valid ? v.y : 0.f;
+                        }
+                        cf p0 = cmul(x[0], q[0]);
+                        cf acc = p0;
+    #pragma unroll
+                        for (int j = 1; j < 16; ++j) {
+                            acc.x = fmaf(x[j].x, q[j].x, acc.x);
+                            acc.x = fmaf(-x[j].y, q[j].y, acc.x);
+                            acc.y = fmaf(x[j].x, q[j].y, acc.y);
+                            acc.y = fmaf(x[j].y, q[j].x, acc.y);
+                        }
+                        if (!inB) p0 = cf{0.f, 0.f};
+                        part[(k - k0) * 128 + t] = make_float4(acc.x, acc.y, p0.x, p0.y);
+                    }
+                    __syncthreads();
+                    {   // reduce the staged rows: warp w takes rows w, w+4, ...
+                        const int w = t >> 5, l = t & 31;
+                        for (int r = w; r < k1 - k0; r += 4) {
+                            float4 v = part[r * 128 + l];
+    #pragma unroll
+                            for (int m = 1; m < 4; ++m) {
+                                const float4 u = part[r * 128 + l + 32 * m];
+                                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+                            }
+                            v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
+                            if (l == 0) S->red[k0 + r] = v;
+                        }
+                    }
+                    __syncthreads();
+                }
             }
             if (kStage && t == 0 && e + 1 < a.n_epochs)      // the prompt pass was the last reader of this epoch's block
                 trk_stage_issue(stage, rec_base + (long long)(e + 1) * epoch_bytes, epoch_bytes, &S->rawbar);
