@@ -128,7 +128,12 @@ struct TrackSmem {
     float sh_f[8];
     int sh_i[8];
     float nb[2];                         // corr[mx-1], corr[mx+1]
-    double pr_re[GR_MAX_PROMPT], pr_im[GR_MAX_PROMPT];   // prompt means (complex128 in the reference)
+    double pr_re[3][GR_MAX_PROMPT], pr_im[3][GR_MAX_PROMPT];   // prompt means (complex128 in the reference), one copy per tail warp
+    float4 wxs[3][GR_MAX_NCYC + 2];      // (X_k, XB_k) per tail warp
+    float qsum[6];                       // qred summed over the warps
+    double carry0_re, carry0_im;         // PREV_SAMPLES at the start of the epoch (the tail warps read these, warp 0 writes the new ones)
+    double min_edge;                     // 3 STD_DEV of the previous epoch
+    int carry0_cnt, locked_in, do_sweep;
     float ph[GR_MAX_PROMPT + 2];         // phase / realPhase
     // epoch scalars (written by thread 0, read by all after a barrier)
     float w32, phase32;
@@ -180,6 +185,18 @@ __device__ __forceinline__ cf expmi_d(double a) {   // exp(-i a), argument reduc
     return expmi((float)a);
 }
 
+// fmodf(p, float32(2 pi)) for |p| < 2^20 without the generic remainder loop: the quotient from one FP64 multiply (it may
+// be off by one), the remainder p - q m exactly by one FP64 FMA (q m has <= 44 significant bits), then the off-by-one
+// fix-up; the result is exactly representable in float32, like fmodf's.
+__device__ __forceinline__ float fmod_2pi_f32(float p) {
+    const double m = (double)GR_TWO_PI_F;
+    const double q = trunc((double)p * (1.0 / (double)GR_TWO_PI_F));
+    double r = fma(-q, m, (double)p);
+    if (p >= 0.f) { if (r < 0.0) r += m; else if (r >= m) r -= m; }
+    else { if (r > 0.0) r -= m; else if (r <= -m) r += m; }
+    return (float)r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -187,7 +204,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---- correlation: folded samples F (natural FFT layout) -> statistics of |ifft(fft(F)/avg * conjC)| --
-// Leaves mx in S->sh_i[4], z / mean / std / corr[mx-1..mx+1] in S; ends with a barrier.
+// Leaves mx in S->sh_i[4], z / mean / std / corr[mx-1..mx+1] in S, written by thread 0; the caller synchronises.
 template <bool kOneBuf>
 __device__ __forceinline__ void corr_and_stats(cf* F, const float2* __restrict__ cs, float scale, cf* fftbuf,
                                                const cf* tw1, const cf* tw2, int t, TrackSmem* S) {
@@ -243,27 +260,30 @@ __device__ __forceinline__ void corr_and_stats(cf* F, const float2* __restrict__
     }
     __syncthreads();
     if (t == 0) {
-        const double mean = sum / GR_N;
-        double var = sum2 / GR_N - mean * mean;
+        const double mean = sum * (1.0 / GR_N);
+        double var = sum2 * (1.0 / GR_N) - mean * mean;
         var = var > 0.0 ? var : 0.0;
+        const float sd = sqrtf((float)var);          // float sqrt / divide: the double versions are ~500 cycles of this one thread
         S->cmean = mean;
-        S->cstd = sqrt(var);
-        S->z = ((double)bm - mean) / S->cstd;
+        S->cstd = (double)sd;
+        S->z = (double)((float)((double)bm - mean) / sd);
         S->c3[0] = S->nb[0];
         S->c3[1] = bm;
         S->c3[2] = S->nb[1];
         S->sh_i[4] = bi;
     }
-    __syncthreads();
+    // no barrier: thread 0 goes on with the decision; the caller synchronises
 }
 
 // gpslib.py:1268-1290 fitCodePhase (double arithmetic on the float32 correlation values)
+// The three values are float32 correlation magnitudes; their differences are formed in double (exact), the two
+// quotients in float32 (6e-8 relative: 3e-8 sample, against the 7e-4 sample = 0.1 m bound) -- two FP64 divisions would be
+// ~300 cycles on the epoch's critical path.
 __device__ __forceinline__ double fit_code_phase(int mx, double lo, double c, double hi) {
-    double tri;
-    if (lo > hi) tri = 0.5 * (hi - lo) / (c - hi);
-    else tri = 0.5 * (hi - lo) / (c - lo);
-    const double par = 0.5 * (hi - lo) / (2.0 * c - hi - lo);
-    return (double)mx + 0.5 * (tri + par);
+    const float num = (float)(0.5 * (hi - lo));
+    const float tri = num / (float)(lo > hi ? c - hi : c - lo);
+    const float par = num / (float)(2.0 * c - hi - lo);
+    return (double)mx + 0.5 * ((double)tri + (double)par);
 }
 
 // Coherent fold of `nblk` 1-ms blocks starting at block `first` (natural FFT layout):
@@ -421,21 +441,30 @@ __device__ __forceinline__ void st_init_sweep(GrChanHot* c, GrChan* g, const gr_
 // of its last NO_SEC entries, kept as exact integer running sums.  At n_cyc = 8 the list's capacity equals the ring's
 // (60 * 128), so the slot the new entry goes into can be the one that holds the oldest entry: both entries that leave a
 // sum are read BEFORE the store.
+__device__ __forceinline__ void st_corr_ratios(GrChanHot* c, int no_sec) {          // the two means (FP64 divisions)
+    c->corr_q = (double)c->cl_sum / (double)c->cl_len;
+    const int nl = c->cl_len < no_sec ? c->cl_len : no_sec;
+    c->corr_l = (double)c->cl_sum_last / (double)nl;
+}
+template <bool kRatios = true>
 __device__ __forceinline__ void st_corr_quality(GrChanHot* c, GrChan* g, double code_phase, int no_sec) {
     const int cap = 60 * no_sec;
     const int v = code_phase < 0.0 ? -1 : 1;
     const int len = c->cl_len, head = c->cl_head;
     const bool full = len + 1 > cap;                       // append, then pop the oldest
     const int out_all = full ? (int)g->cl[head] : 0;
-    const int out_win = (len + 1 > no_sec) ? (int)g->cl[(head + len - no_sec) % GR_CL_CAP] : 0;
-    g->cl[(head + len) % GR_CL_CAP] = (int8_t)v;
+    // head, len <= GR_CL_CAP: the ring indices are below 2 GR_CL_CAP, one conditional subtraction instead of a modulo
+    int iw = head + len - no_sec, is = head + len, ih = head + 1;
+    iw -= iw >= GR_CL_CAP ? GR_CL_CAP : 0;
+    is -= is >= GR_CL_CAP ? GR_CL_CAP : 0;
+    ih -= ih >= GR_CL_CAP ? GR_CL_CAP : 0;
+    const int out_win = (len + 1 > no_sec) ? (int)g->cl[iw] : 0;
+    g->cl[is] = (int8_t)v;
     c->cl_sum += v - out_all;
     c->cl_sum_last += v - out_win;
-    if (full) c->cl_head = (head + 1) % GR_CL_CAP;
+    if (full) c->cl_head = ih;
     else c->cl_len = len + 1;
-    c->corr_q = (double)c->cl_sum / (double)c->cl_len;
-    const int nl = c->cl_len < no_sec ? c->cl_len : no_sec;
-    c->corr_l = (double)c->cl_sum_last / (double)nl;
+    if (kRatios) st_corr_ratios(c, no_sec);
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
@@ -480,6 +509,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
     const int n_cyc = a.cfg.n_cyc;
     const int ngps = n_cyc * GR_N;
     const int no_sec = 1024 / n_cyc;
+    const int ngps_sh = 31 - __clz(ngps);
     const int corr_avg = a.cfg.corr_avg < n_cyc ? a.cfg.corr_avg : n_cyc;
     const int prn = Gg->h.prn;
     const float2* cs = a.tab.conjspec + (size_t)prn * GR_N;
@@ -512,11 +542,11 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
         const void* src = kStage ? (const void*)stage
                                  : (const void*)(rec_base + (long long)e * ngps * (IN_FMT == GR_IN_U8IQ ? 2 : 8));
         const long long smp_time = a.smp_time + (long long)e * ngps;
-        const long long stream_no = smp_time / ngps;
+        const long long stream_no = smp_time >> ngps_sh;            // ngps and no_sec are powers of two (n_cyc = 8, 16, 32)
         gr_epoch_out* gO = a.out + ((size_t)e * a.n_active + blockIdx.x);
         gr_epoch_out* O = &S->out[e & 1];       // assembled in shared memory: no global store sits in front of a barrier
         if (t == 0 && a.out_tma) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // record e-2 has left
-        const bool report = (stream_no % no_sec) == 0;
+        const bool report = (stream_no & (long long)(no_sec - 1)) == 0;
 
         // ---- epoch prologue (gpslib.py:1142-1151) ----
         if (t == 0) {
@@ -528,6 +558,10 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
             if (req) { st_init_sweep(C, G, a.cfg); erased = 1; }
             O->erased = erased;
             S->branch_sweep = C->sweep;
+            S->carry0_cnt = C->carry_cnt; S->carry0_re = C->carry_re; S->carry0_im = C->carry_im;
+            S->min_edge = C->std_weak ? 3.0 * C->std_dev : (double)__fmul_rn(3.0f, (float)C->std_dev);
+            S->locked_in = C->locked;
+            S->do_sweep = 0;
             S->dq = C->delay >> 3;
             S->w32 = weak_w32(C->freq, C->freq_weak);
             S->phase32 = C->phase;
@@ -558,6 +592,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                 cf F[16];
                 fold_blocks<IN_FMT, kStage>(F, src, 0, avg, rt, t, S);
                 corr_and_stats<kDense>(F, cs, 1.0f / ((float)avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
+                __syncthreads();
                 z = S->z;
                 if (z > (double)a.cfg.corr_min) {
                     delay = S->sh_i[4];
@@ -638,18 +673,20 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                 fold_blocks<IN_FMT, kStage>(F, src, (n_cyc - corr_avg) / 2, corr_avg, rt, t, S);
                 corr_and_stats<kDense>(F, cs, 1.0f / ((float)corr_avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
             }
-            if (t == 0) {
+            if (t == 0) {                                    // same thread as the statistics above: no barrier in between
                 int delay = -1;
                 double code_phase = -1.0;
                 if (S->z > (double)a.cfg.corr_min) {
                     delay = S->sh_i[4];
                     code_phase = fit_code_phase(delay, (double)S->c3[0], (double)S->c3[1], (double)S->c3[2]);
                 }
-                st_corr_quality(C, G, code_phase, no_sec);
+                st_corr_quality<false>(C, G, code_phase, no_sec);      // integer sums now, the two FP64 means by thread 96 later
                 if (delay >= 0) C->delay = delay;
                 S->corr_delay = delay;
                 S->code_phase = code_phase;
                 S->delay = C->delay;
+                const int dd = C->delay;
+                S->n_prompt = ((C->carry_cnt + dd > 0) ? 1 : 0) + (n_cyc - 1) + (dd == 0 ? 1 : 0);
             }
             __syncthreads();
 
@@ -748,6 +785,8 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                         S->red[t].z = bsum.x;
                         S->red[t].w = bsum.y;
                     }
+                    if (k0 == 0 && t >= 96 && t < 102)
+                        S->qsum[t - 96] = (S->qred[0][t - 96] + S->qred[1][t - 96]) + (S->qred[2][t - 96] + S->qred[3][t - 96]);
                     {   // reduce the staged rows: warp w takes rows w, w+4, ...
                         const int w = t >> 5, l = t & 31;
                         for (int r = w; r < k1 - k0; r += 4) {
@@ -819,6 +858,8 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                         part[(k - k0) * 128 + t] = make_float4(acc.x, acc.y, p0.x, p0.y);
                     }
                     __syncthreads();
+                    if (k0 == 0 && t >= 96 && t < 102)
+                        S->qsum[t - 96] = (S->qred[0][t - 96] + S->qred[1][t - 96]) + (S->qred[2][t - 96] + S->qred[3][t - 96]);
                     {   // reduce the staged rows: warp w takes rows w, w+4, ...
                         const int w = t >> 5, l = t & 31;
                         for (int r = w; r < k1 - k0; r += 4) {
@@ -837,116 +878,226 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
             }
             if (kStage && t == 0 && e + 1 < a.n_epochs)      // the prompt pass was the last reader of this epoch's block
                 trk_stage_issue(stage, rec_base + (long long)(e + 1) * epoch_bytes, epoch_bytes, &S->rawbar);
-            // true-sample sums X_k, XB_k (threads 0..n_cyc), then the per-ms means (thread 0)
-            if (t <= n_cyc) {
-                const int k = t;
-                const float4 v = S->red[k];
-                float qs[6];
-#pragma unroll
-                for (int m = 0; m < 6; ++m) qs[m] = (S->qred[0][m] + S->qred[1][m]) + (S->qred[2][m] + S->qred[3][m]);
-                const cf Qk = (k == 0) ? cf{qs[4], qs[5]} : (k == n_cyc ? cf{qs[0] - qs[4], qs[1] - qs[5]} : cf{qs[0], qs[1]});
-                cf X = affine_sum<IN_FMT>(cf{v.x, v.y}, Qk);
-                cf XB = (k == 0) ? cf{0.f, 0.f} : affine_sum<IN_FMT>(cf{v.z, v.w}, cf{qs[2], qs[3]});
-                const cf R = S->Rm[k];
-                X = cmul(X, R);
-                XB = cmul(XB, R);
-                S->xs[k] = make_float4(X.x, X.y, XB.x, XB.y);
-            }
-            __syncthreads();
-            // seg_m = X_m - XB_m + XB_{m+1} (m < n_cyc), tail = X_n - XB_n; one segment per thread (the FP64
-            // divisions run in parallel), prompt index = (first segment present ? 1 : 0) + m - 1
-            const int nps0 = C->carry_cnt;
+            // ---- everything behind the prompt sums is split by TASK over the four warps, warp-level synchronisation only:
+            //      warp 0 the carrier loop (the only part the next epoch waits for), warp 1 the edge detector, warp 2 the
+            //      amplitude statistics and the prompt values of the record, warp 3 the remaining record fields.  Warps 0-2
+            //      each form the 1-ms prompt means themselves (lane k <-> pass k, and k + 32) -- same arithmetic, same bits --
+            //      so that no block barrier sits between the sums and their three consumers.  State is partitioned by
+            //      warp; what one warp needs from another's previous value was snapshot in the prologue.
+            const int np = S->n_prompt;
+            const int wid = t >> 5, ln = t & 31;
+            const unsigned FULL = 0xffffffffu;
+            const int nps0 = S->carry0_cnt;
             const bool first_present = nps0 + d > 0;
-            const int np_total = (first_present ? 1 : 0) + (n_cyc - 1) + (d == 0 ? 1 : 0);
-            double tail_re = 0.0, tail_im = 0.0;
-            if (t <= n_cyc) {
-                const int m = t;
-                const float4 v = S->xs[m];
-                double sre = (double)v.x - (double)v.z, sim = (double)v.y - (double)v.w;
-                if (m < n_cyc) { const float4 u = S->xs[m + 1]; sre += (double)u.z; sim += (double)u.w; }
-                if (m == 0) {
-                    if (first_present) {
-                        const int cnt = nps0 + d;
-                        S->pr_re[0] = (C->carry_re + sre) / (double)cnt;
-                        S->pr_im[0] = (C->carry_im + sim) / (double)cnt;
-                    }
-                } else if (m < n_cyc || d == 0) {
-                    const int idx = (first_present ? 1 : 0) + m - 1;
-                    S->pr_re[idx] = sre / (double)GR_N;
-                    S->pr_im[idx] = sim / (double)GR_N;
-                } else {
-                    tail_re = sre;
-                    tail_im = sim;
-                }
-            }
-            __syncthreads();
-            if (t == n_cyc) {                                  // carry-over of the partial code period (gpslib.py:1440-1441)
-                if (d == 0) { C->carry_cnt = 0; C->carry_re = 0.0; C->carry_im = 0.0; }
-                else { C->carry_cnt = GR_N - d; C->carry_re = tail_re; C->carry_im = tail_im; }
-            }
-            if (t == 0) {
-                const int nps = nps0;
-                int n1 = nps + d;
-                long long st;
-                if (n1 == 0) { n1 = GR_N; st = smp_time; } else { st = smp_time + d - GR_N; }
-                const int np = np_total;
-                S->n_prompt = np;
-                // ---- edge detector (gpslib.py:1417-1436), threshold from the PREVIOUS epoch's STD_DEV ----
-                unsigned long long mask = 0ull;
-                if (C->locked) {
-                    const double min_edge = C->std_weak ? 3.0 * C->std_dev : (double)__fmul_rn(3.0f, (float)C->std_dev);
-                    int edge0 = C->edge0, elen = C->edge_len;
-                    double prev_sign = (double)((2 * (elen % 2) - 1) * edge0);
-                    double prev_signal = C->prev_signal;
-                    for (int k = 0; k < np; ++k) {
-                        const double mr = S->pr_re[k];
-                        const double s = mr > 0.0 ? 1.0 : (mr < 0.0 ? -1.0 : 0.0);
-                        if (edge0 == 0) {
-                            edge0 = (int)s;
-                            prev_sign = s;
-                        } else if (s != prev_sign && prev_sign * prev_signal > 0.0 && fabs(mr - prev_signal) > min_edge) {
-                            mask |= 1ull << k;
-                            ++elen;
-                            prev_sign = s;
-                        }
-                        prev_signal = mr;
-                    }
-                    C->edge0 = edge0;
-                    C->edge_len = elen;
-                    C->prev_signal = prev_signal;
-                    C->ms_time += np;
-                }
-                O->edge_mask = mask;
-                O->n_prompt = np;
-                O->prompt_b1 = n1;
-                O->prompt_st0 = st;
-            }
-            __syncthreads();
-
-            // ---- amplitude statistics + PLL (warp 0), gpslib.py:1186-1188, 1215-1262 ----
-            if (t < 32) {
-                const int np = S->n_prompt;
-                float ph[2], ab[2];
+            const int fp = first_present ? 1 : 0;
+            double mr[2] = {0.0, 0.0}, mi[2] = {0.0, 0.0};              // this lane's prompts: index ln and ln + 32
+            if (wid < 3) {
+                float4* xsw = S->wxs[wid];
+                double* prr = S->pr_re[wid];
+                double* pri = S->pr_im[wid];
+                // true-sample sums X_k, XB_k: affine map per sum, block rotation R_{k-1}
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int k = t + 32 * h;
-                    ph[h] = 0.f; ab[h] = 0.f;
-                    if (k >= np && k < GR_MAX_PROMPT) { O->prompt[2 * k] = 0.f; O->prompt[2 * k + 1] = 0.f; }
+                    const int k = ln + 32 * h;
+                    if (k <= n_cyc) {
+                        const float4 v = S->red[k];
+                        const cf Qk = (k == 0) ? cf{S->qsum[4], S->qsum[5]}
+                                               : (k == n_cyc ? cf{S->qsum[0] - S->qsum[4], S->qsum[1] - S->qsum[5]} : cf{S->qsum[0], S->qsum[1]});
+                        cf X = affine_sum<IN_FMT>(cf{v.x, v.y}, Qk);
+                        cf XB = (k == 0) ? cf{0.f, 0.f} : affine_sum<IN_FMT>(cf{v.z, v.w}, cf{S->qsum[2], S->qsum[3]});
+                        const cf R = S->Rm[k];
+                        X = cmul(X, R);
+                        XB = cmul(XB, R);
+                        xsw[k] = make_float4(X.x, X.y, XB.x, XB.y);
+                    }
+                }
+                __syncwarp();
+                // seg_m = X_m - XB_m + XB_{m+1} (m < n_cyc), tail = X_n - XB_n; prompt index = (first segment present ? 1 : 0) + m - 1
+                // 1 / (number of samples of the first, partial segment): float reciprocal + two Newton steps in FP64 (the FP64
+                // division is ~150 cycles; the quotient differs from the correctly rounded one by at most 1 ulp of a double)
+                const double cnt = (double)(nps0 + d > 0 ? nps0 + d : 1);
+                double rc = (double)__frcp_rn((float)cnt);
+                rc = rc * (2.0 - cnt * rc);
+                rc = rc * (2.0 - cnt * rc);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int m = ln + 32 * h;
+                    if (m <= n_cyc) {
+                        const float4 v = xsw[m];
+                        double sre = (double)v.x - (double)v.z, sim = (double)v.y - (double)v.w;
+                        if (m < n_cyc) { const float4 u = xsw[m + 1]; sre += (double)u.z; sim += (double)u.w; }
+                        if (m == 0) {
+                            if (first_present) { prr[0] = (S->carry0_re + sre) * rc; pri[0] = (S->carry0_im + sim) * rc; }
+                        } else if (m < n_cyc || d == 0) {
+                            prr[fp + m - 1] = sre * (1.0 / GR_N);                     // exact: a power of two
+                            pri[fp + m - 1] = sim * (1.0 / GR_N);
+                        } else if (wid == 0) {                                        // carry-over of the partial code period (gpslib.py:1440-1441)
+                            C->carry_cnt = GR_N - d; C->carry_re = sre; C->carry_im = sim;
+                        }
+                        if (wid == 0 && m == n_cyc && d == 0) { C->carry_cnt = 0; C->carry_re = 0.0; C->carry_im = 0.0; }
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = ln + 32 * h;
+                    if (k < np) { mr[h] = prr[k]; mi[h] = pri[k]; }
+                }
+            }
+            if (wid == 1) {
+                // ---- edge detector (gpslib.py:1417-1436), threshold from the PREVIOUS epoch's STD_DEV.  The per-prompt
+                //      comparisons run one per lane; what is sequential (the sign of the last accepted edge) is a loop over
+                //      ballot masks in registers ----
+                unsigned long long emask = 0ull;
+                if (S->locked_in) {
+                    const double* prr = S->pr_re[1];
+                    const double min_edge = S->min_edge;
+                    const double prev_signal0 = C->prev_signal;
+                    unsigned long long pos = 0ull, neg = 0ull, ppos = 0ull, pneg = 0ull, big = 0ull;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int k = ln + 32 * h;
+                        const bool valid = k < np;
+                        const double prev = (k == 0) ? prev_signal0 : (valid ? prr[k - 1] : 0.0);
+                        pos |= (unsigned long long)__ballot_sync(FULL, valid && mr[h] > 0.0) << (32 * h);
+                        neg |= (unsigned long long)__ballot_sync(FULL, valid && mr[h] < 0.0) << (32 * h);
+                        ppos |= (unsigned long long)__ballot_sync(FULL, valid && prev > 0.0) << (32 * h);
+                        pneg |= (unsigned long long)__ballot_sync(FULL, valid && prev < 0.0) << (32 * h);
+                        big |= (unsigned long long)__ballot_sync(FULL, valid && fabs(mr[h] - prev) > min_edge) << (32 * h);
+                    }
+                    int edge0 = C->edge0, elen = C->edge_len;
+                    int prev_sign = (2 * (elen & 1) - 1) * edge0;
+                    const unsigned long long all = np >= 64 ? ~0ull : ((1ull << np) - 1ull);
+                    if (edge0 != 0 && (pos | neg) == all && (ppos | pneg) == all && np <= 32) {
+                        // the usual case: every sign is +-1.  One bit of state (the sign of the last accepted edge), masks shifted
+                        // down one position per prompt
+                        unsigned s32 = (unsigned)pos, p32 = (unsigned)ppos, b32 = (unsigned)big, ps = prev_sign > 0 ? 1u : 0u, em = 0u;
+                        for (int k = 0; k < np; ++k) {
+                            const unsigned sb = s32 & 1u, edge = (sb ^ ps) & ~(ps ^ (p32 & 1u)) & b32 & 1u;
+                            em |= edge << k;
+                            ps ^= edge;                                   // an accepted edge flips the sign
+                            s32 >>= 1; p32 >>= 1; b32 >>= 1;
+                        }
+                        emask = em;
+                        elen += __popc(em);
+                    } else {
+                        for (int k = 0; k < np; ++k) {
+                            const int sgn = (int)((pos >> k) & 1ull) - (int)((neg >> k) & 1ull);
+                            if (edge0 == 0) {
+                                edge0 = sgn;
+                                prev_sign = sgn;
+                            } else {
+                                const bool same = prev_sign > 0 ? ((ppos >> k) & 1ull) != 0 : (prev_sign < 0 ? ((pneg >> k) & 1ull) != 0 : false);
+                                if (sgn != prev_sign && same && ((big >> k) & 1ull)) {
+                                    emask |= 1ull << k;
+                                    ++elen;
+                                    prev_sign = sgn;
+                                }
+                            }
+                        }
+                    }
+                    if (report && elen > 2) {                        // evalEdges -> logicalBits, gpslib.py:1465-1487 (runs while still PHASE_LOCKED as of this epoch's start)
+                        if ((elen - 2) & 1) edge0 = -edge0;
+                        elen = 2;
+                    }
+                    if (ln == 0) {
+                        C->edge0 = edge0;
+                        C->edge_len = elen;
+                        if (np > 0) C->prev_signal = prr[np - 1];
+                        C->ms_time += np;
+                    }
+                }
+                if (ln == 0) {
+                    int n1 = nps0 + d;
+                    long long st;
+                    if (n1 == 0) { n1 = GR_N; st = smp_time; } else { st = smp_time + d - GR_N; }
+                    O->edge_mask = emask;
+                    O->prompt_b1 = n1;
+                    O->prompt_st0 = st;
+                    O->edge0 = C->edge0;
+                    O->edge_len = C->edge_len;
+                    O->ms_time = C->ms_time;
+                }
+            } else if (wid == 2) {
+                // ---- amplitude statistics (gpslib.py:1186-1188) and the prompt values of the record ----
+                float ab[2];
+                float sum_ab = 0.f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = ln + 32 * h;
+                    ab[h] = 0.f;
                     if (k < np) {
-                        const cf g = cf{(float)S->pr_re[k], (float)S->pr_im[k]};      // np.asarray(..., complex64)
+                        const cf g = cf{(float)mr[h], (float)mi[h]};                   // gpsData = np.asarray(..., complex64)
                         O->prompt[2 * k] = g.x;
                         O->prompt[2 * k + 1] = g.y;
-                        ph[h] = atanf(__fdiv_rn(g.y, g.x));
                         ab[h] = hypotf(g.x, g.y);
+                        sum_ab += ab[h];
+                    } else if (k < GR_MAX_PROMPT) {
+                        O->prompt[2 * k] = 0.f;
+                        O->prompt[2 * k + 1] = 0.f;
+                    }
+                }
+                if (ln < 2 && ln + 32 >= np) { O->prompt[2 * (ln + 32)] = 0.f; O->prompt[2 * (ln + 32) + 1] = 0.f; }
+                sum_ab = warp_sum(sum_ab);
+                const float fn = (float)np;
+                const float mean_ab = sum_ab / fn;
+                float sq = 0.f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = ln + 32 * h;
+                    if (k < np) { const float dv = ab[h] - mean_ab; sq = fmaf(dv, dv, sq); }
+                }
+                sq = warp_sum(sq);
+                if (ln == 0) {
+                    const float std32 = sqrtf(sq / fn);
+                    const float amp = mean_ab / std32;
+                    C->std_dev = (double)std32;
+                    C->std_weak = 0;
+                    C->amplitude = amp;
+                    O->amplitude = amp;
+                    O->std_dev = std32;
+                }
+            } else if (wid == 3) {
+                if (ln == 0) {                                       // CORR_Q, CORR_L: two FP64 divisions, off the critical path
+                    st_corr_ratios(C, no_sec);
+                    O->corr_q = C->corr_q;
+                    O->corr_l = C->corr_l;
+                } else if (ln == 1) {
+                    O->tracked = 1;
+                    O->corr_delay = S->corr_delay;
+                    O->code_phase = S->code_phase;
+                    O->corr3[0] = S->c3[0]; O->corr3[1] = S->c3[1]; O->corr3[2] = S->c3[2];
+                    O->corr_mean = (float)S->cmean;
+                    O->corr_std = (float)S->cstd;
+                    O->n_prompt = np;
+                    O->delay = d;
+                    O->n_prev = d == 0 ? 0 : GR_N - d;
+                    C->max_corr = S->z;
+                    O->max_corr = S->z;
+                    O->reserved[0] = 0; O->reserved[1] = 0;
+                }
+            } else {
+                // ---- carrier loop: phaseLockedLoop, gpslib.py:1215-1262 ----
+                float ph[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = ln + 32 * h;
+                    ph[h] = 0.f;
+                    if (k < np) {
+                        ph[h] = atanf(__fdiv_rn((float)mi[h], (float)mr[h]));
                         S->ph[k] = ph[h];
                     }
                 }
+                // mean of the DF FIFO (its loads issue before the scan below)
+                float dsum = 0.f;
+                const int dfl = C->df_len, dfh = C->df_head;
+                for (int i = ln; i < dfl; i += 32) dsum += G->df[(dfh + i) % GR_DF_CAP];
                 __syncwarp();
                 // unwrap: dp -= sign(delta) whenever |delta| > 2; realPhase[i] += dp*pi
                 float inc[2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int k = t + 32 * h;
+                    const int k = ln + 32 * h;
                     inc[h] = 0.f;
                     if (k >= 1 && k < np) {
                         const float dl = __fsub_rn(ph[h], S->ph[k - 1]);
@@ -956,71 +1107,44 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                 float sc = inc[0];                       // inclusive scan: elements 0..31
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const float u = __shfl_up_sync(0xffffffffu, sc, o);
-                    if (t >= o) sc += u;
+                    const float u = __shfl_up_sync(FULL, sc, o);
+                    if (ln >= o) sc += u;
                 }
-                const float tot31 = __shfl_sync(0xffffffffu, sc, 31);
-                const float inc32 = __shfl_sync(0xffffffffu, inc[1], 0);
+                const float tot31 = __shfl_sync(FULL, sc, 31);
+                const float inc32 = __shfl_sync(FULL, inc[1], 0);
                 float turns[2];
                 turns[0] = sc;
-                turns[1] = tot31 + inc32 + (t == 1 ? inc[1] : 0.f);     // element 32 (lane 0), 33 (lane 1)
+                turns[1] = tot31 + inc32 + (ln == 1 ? inc[1] : 0.f);     // element 32 (lane 0), 33 (lane 1)
                 __syncwarp();
-                float sum_rp = 0.f, sum_ab = 0.f;
+                float sum_rp = 0.f;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int k = t + 32 * h;
+                    const int k = ln + 32 * h;
                     if (k < np) {
                         const float rp = __fadd_rn(ph[h], __fmul_rn(turns[h], GR_PI_F));
                         S->ph[k] = rp;
                         sum_rp += rp;
-                        sum_ab += ab[h];
                     }
                 }
-                sum_rp = warp_sum(sum_rp);
-                sum_ab = warp_sum(sum_ab);
-                const float fn = (float)np;
-                const float mean_ab = sum_ab / fn;
-                float sq = 0.f;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int k = t + 32 * h;
-                    if (k < np) { const float dv = ab[h] - mean_ab; sq = fmaf(dv, dv, sq); }
+                for (int o = 16; o > 0; o >>= 1) {       // two independent butterflies interleaved
+                    sum_rp += __shfl_xor_sync(FULL, sum_rp, o);
+                    dsum += __shfl_xor_sync(FULL, dsum, o);
                 }
-                sq = warp_sum(sq);
-                // mean of the DF FIFO
-                float dsum = 0.f;
-                const int dfl = C->df_len, dfh = C->df_head;
-                for (int i = t; i < dfl; i += 32) dsum += G->df[(dfh + i) % GR_DF_CAP];
-                dsum = warp_sum(dsum);
                 __syncwarp();
-                if (t == 0) {
-                    const float std32 = sqrtf(sq / fn);
-                    C->std_dev = (double)std32;
-                    C->std_weak = 0;
-                    C->amplitude = mean_ab / std32;
-                    C->max_corr = S->z;
-                    O->tracked = 1;
-                    O->corr_delay = S->corr_delay;
-                    O->code_phase = S->code_phase;
-                    O->corr3[0] = S->c3[0]; O->corr3[1] = S->c3[1]; O->corr3[2] = S->c3[2];
-                    O->corr_mean = (float)S->cmean;
-                    O->corr_std = (float)S->cstd;
+                if (ln == 0) {
+                    const float fn = (float)np;
                     bool sweep = false;
                     if (report) {
                         O->rep_sweep = C->rep_sweep;
                         O->report_freq = C->freq;
                         C->rep_sweep = 0;
-                        if (C->locked && C->edge_len > 2) {          // evalEdges -> logicalBits, gpslib.py:1465-1487
-                            if ((C->edge_len - 2) & 1) C->edge0 = -C->edge0;
-                            C->edge_len = 2;
-                        }
-                        if (C->cl_len >= 60 * no_sec) sweep = C->corr_q < -0.9;   // checkCorrQuality
+                        if (C->cl_len >= 60 * no_sec)                // checkCorrQuality (CORR_Q itself is warp 3's job: same quotient)
+                            sweep = (double)C->cl_sum / (double)C->cl_len < -0.9;
                     }
                     if (sweep) {
-                        st_init_sweep(C, G, a.cfg);
-                        O->erased |= 2;
+                        S->do_sweep = 1;                             // initSweep touches every warp's state: after the barrier below
                     } else {
-                        // phaseLockedLoop
                         const float max_df = 20.0f / (float)no_sec;
                         const float dev = sum_rp / fn;
                         const int n4 = np < 4 ? np : 4;
@@ -1041,8 +1165,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                         if (fabsf(dev) < 0.1f) C->locked = 1;
                         // demodDoppler's phase carry (gpslib.py:1345-1346), then PHASE += phaseshift
                         const float tlast = __fdiv_rn((float)ngps, GR_FS);
-                        float p = __fadd_rn(phase32, __fmul_rn(w32, tlast));
-                        p = fmodf(p, GR_TWO_PI_F);
+                        float p = fmod_2pi_f32(__fadd_rn(phase32, __fmul_rn(w32, tlast)));
                         if (p < 0.f) p += GR_TWO_PI_F;
                         C->phase = __fadd_rn(p, off);
                         const float f = __fadd_rn((float)C->freq, df);
@@ -1050,11 +1173,17 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                         else if (f < a.cfg.min_freq) { C->freq = (double)a.cfg.min_freq; C->freq_weak = 1; }
                         else { C->freq = (double)f; C->freq_weak = 0; }
                     }
+                    O->sweep = 0;
+                    O->locked = C->locked;
+                    O->freq = C->freq;
+                    O->freq_weak = C->freq_weak;
+                    O->phase = (double)C->phase;
                 }
             }
         }
-        // no barrier here: everything below was produced by thread 0 itself (the loop filter / sweep bookkeeping above)
-        if (t == 0) {
+        // sweep branch: thread 0 produced everything itself (no barrier needed in front of this copy); tracking branch: the
+        // four warps have written their record fields directly
+        if (t == 0 && S->branch_sweep) {
             // all loads first: C and O are both shared memory, the compiler will not reorder loads over stores
             const int v_sweep = C->sweep, v_delay = C->delay, v_locked = C->locked, v_ms = C->ms_time, v_prev = C->carry_cnt;
             const int v_weak = C->freq_weak, v_e0 = C->edge0, v_el = C->edge_len;
@@ -1077,10 +1206,26 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
             O->std_dev = (float)v_sd;
             O->reserved[0] = 0; O->reserved[1] = 0;
         }
-        // the record was written through the generic proxy by warp 0 only (thread 0 and the PLL lanes): its fence
-        // orders those writes before the bulk copy; the other warps do not pay for a fence
-        if (t < 32) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // the record was written through the generic proxy: every writer's fence orders its writes before the bulk copy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        if (S->do_sweep) {                                   // quality-triggered re-sweep (gpslib.py:1134-1138, 1198-1203): rare; uniform
+            if (t == 0) {
+                st_init_sweep(C, G, a.cfg);
+                O->erased |= 2;
+                O->sweep = C->sweep;
+                O->locked = C->locked;
+                O->ms_time = C->ms_time;
+                O->n_prev = C->carry_cnt;
+                O->freq = C->freq;
+                O->freq_weak = C->freq_weak;
+                O->edge0 = C->edge0;
+                O->edge_len = C->edge_len;
+                O->phase = (double)C->phase;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            __syncthreads();
+        }
         if (a.out_tma) {
             if (t == 0) {
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -1275,7 +1420,7 @@ extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int
     }
     b->last_launches = 0;
     if (b->active.empty()) return GR_OK;
-    if (b->max_rec > 0 && rec_stride < (int64_t)n_epochs * b->cfg.n_cyc * GR_N) {
+    if (b->max_rec > 0 && rec_stride != 0 && rec_stride < (int64_t)n_epochs * b->cfg.n_cyc * GR_N) {   // 0: all channels read the same samples
         gr_set_error("gr_track_process_dev: channels on recordings 0..%d need rec_stride >= %lld samples", b->max_rec,
                      (long long)n_epochs * b->cfg.n_cyc * GR_N);
         return GR_ERR_ARG;
