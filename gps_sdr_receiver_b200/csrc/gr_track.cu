@@ -119,7 +119,7 @@ struct TrackSmem {
     cf Rm[GR_MAX_NCYC + 2];              // Rm[k] = R_{k-1} = exp(-i w (k-1) ms), k = 0..n_cyc
     float4 red[GR_MAX_NCYC + 2];         // reduced prompt rows: (S_k, B_k)
     float4 xs[GR_MAX_NCYC + 2];          // (X_k, XB_k): affine-corrected, block-rotated
-    float qred[4][6];                    // per-warp sums of q: all rows, masked row 0, wrapped rows
+    float qred[8][6];                    // per-warp sums of q: all rows, masked row 0, wrapped rows
     cf sigma[8];                         // vector form: exp(-i w i / fs), i = 0..7
     cf qb[8];                            // vector form: the replica values of the samples between the window start 8 (d >> 3) and d
     cf qbsum;
@@ -205,10 +205,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- correlation: folded samples F (natural FFT layout) -> statistics of |ifft(fft(F)/avg * conjC)| --
 // Leaves mx in S->sh_i[4], z / mean / std / corr[mx-1..mx+1] in S, written by thread 0; the caller synchronises.
-template <bool kOneBuf>
+template <bool kOneBuf, bool kSub = false>
 __device__ __forceinline__ void corr_and_stats(cf* F, const float2* __restrict__ cs, float scale, cf* fftbuf,
                                                const cf* tw1, const cf* tw2, int t, TrackSmem* S) {
-    fft2048<true, 1, kOneBuf>(F, fftbuf, tw1, tw2, t);
+    // kSub: the 128 threads of this transform are the first half of a 256-thread CTA: named barrier 1 instead of barrier 0
+    auto sync = [&]() { if (kSub) asm volatile("bar.sync 1, 128;" ::: "memory"); else __syncthreads(); };
+    fft2048<!kSub, 1, kOneBuf>(F, fftbuf, tw1, tw2, t);
     cf y[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -216,7 +218,7 @@ __device__ __forceinline__ void corr_and_stats(cf* F, const float2* __restrict__
         y[j].x = F[j].x * c.y + F[j].y * c.x;      // swap form of the inverse transform
         y[j].y = F[j].x * c.x - F[j].y * c.y;
     }
-    fft2048<true, 1, kOneBuf>(y, fftbuf, tw1, tw2, t);
+    fft2048<!kSub, 1, kOneBuf>(y, fftbuf, tw1, tw2, t);
     float st[16];
     float s = 0.f, s2 = 0.f, mx = -1.f;
     int idx = 0;
@@ -239,7 +241,7 @@ __device__ __forceinline__ void corr_and_stats(cf* F, const float2* __restrict__
     }
     const int w = t >> 5;
     if ((t & 31) == 0) { S->sh_d[w] = ds; S->sh_d[4 + w] = ds2; S->sh_f[w] = mx; S->sh_i[w] = idx; }
-    __syncthreads();
+    sync();
     double sum = 0.0, sum2 = 0.0;
     float bm = -1.f;
     int bi = 0;
@@ -258,7 +260,7 @@ __device__ __forceinline__ void corr_and_stats(cf* F, const float2* __restrict__
         if (n == lo) S->nb[0] = st[j];
         if (n == hi) S->nb[1] = st[j];
     }
-    __syncthreads();
+    sync();
     if (t == 0) {
         const double mean = sum * (1.0 / GR_N);
         double var = sum2 * (1.0 / GR_N) - mean * mean;
@@ -338,28 +340,23 @@ __device__ __forceinline__ void load8_u8(const unsigned char* p, cpk* x) {
     }
 }
 // A[8 h + i] = sum_b R_b x_b[8 u_h + i]  (bytes as integers; the affine map is applied to the sum), rsum = sum_b R_b
+template <int NC>
 __device__ __forceinline__ void fold_blocks_vec(cpk* A, cf& rsum, const unsigned char* stage, int first, int nblk, int u0, int u1,
                                                 const cf* Rm) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) A[i] = cpk_make(0.f, 0.f);
+    for (int i = 0; i < 8 * NC; ++i) A[i] = cpk_make(0.f, 0.f);
     rsum = cf{0.f, 0.f};
     for (int b = first; b < first + nblk; ++b) {
         const cf R = Rm[b + 1];
         rsum = cadd(rsum, R);
-        const cpk Rp = cpk_make(R.x, R.y), Rs = cpk_make(-R.y, R.x);      // x R = xr (Rr, Ri) + xi (-Ri, Rr)
         const unsigned char* pb = stage + (size_t)b * (GR_N * 2);
         cpk x[8], y[8];
         load8_u8(pb + 16 * u0, x);
-        load8_u8(pb + 16 * u1, y);
+        if (NC == 2) load8_u8(pb + 16 * u1, y);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float xr, xi, yr, yi;
-            cpk_split(x[i], xr, xi);
-            cpk_split(y[i], yr, yi);
-            A[i] = cpk_fma(cpk_bc(xr), Rp, A[i]);
-            A[8 + i] = cpk_fma(cpk_bc(yr), Rp, A[8 + i]);
-            A[i] = cpk_fma(cpk_bc(xi), Rs, A[i]);
-            A[8 + i] = cpk_fma(cpk_bc(yi), Rs, A[8 + i]);
+        for (int i = 0; i < 8; ++i) {                                      // A += x R: x (Rr, Rr) + swap(x) (-Ri, Ri), two FFMA2
+            A[i] = cpk_mac(A[i], x[i], R.x, R.y);
+            if (NC == 2) A[8 + i] = cpk_mac(A[8 + i], y[i], R.x, R.y);
         }
     }
 }
@@ -492,8 +489,10 @@ __device__ __forceinline__ void trk_stage_issue(void* dst, const char* gsrc, uns
 // the previous epoch's serial tail (prompt means, edge detector, PLL) runs; both sample passes then read
 // shared memory instead of L2/HBM -- a single recording is a chain of dependent epochs, so load latency,
 // not bandwidth, is what the epoch time is made of.
-template <int IN_FMT, bool kStage, bool kDense = false>
-__global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(const TrackArgs a) {
+// NT = 256 ("wide" form, launches of at most one CTA per SM): the two sample passes run on 256 threads with one chunk per
+// thread and block; the transforms and everything serial stay on the first 128 threads (named barrier 1).
+template <int IN_FMT, bool kStage, bool kDense = false, int NT = GR_FFT_THREADS>
+__global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* fftbuf = reinterpret_cast<cf*>(smem_raw);
     float4* part = reinterpret_cast<float4*>(smem_raw);          // aliases the FFT buffers
@@ -501,6 +500,9 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
     unsigned char* stage = smem_raw + a.buf_bytes + ((sizeof(TrackSmem) + 15) & ~(size_t)15);
     GrChanHot* C = &S->CH.h;
     constexpr bool kVec = (IN_FMT == GR_IN_U8IQ) && kStage;      // vector form of the sample passes (staged uint8 I/Q)
+    constexpr int NC = 256 / NT;                                 // chunks per thread and block in the vector form
+    constexpr bool kWide = NT != GR_FFT_THREADS;
+    static_assert(NT == 128 || (NT == 256 && kVec), "the wide form exists for the vector passes only");
 
     const int t = threadIdx.x;
     const int slot = a.slots[blockIdx.x];
@@ -517,13 +519,13 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
     cf tw1[16], tw2[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const float2 u = a.tab.tw1[t * 16 + k];
+        const float2 u = a.tab.tw1[(t & 127) * 16 + k];
         const float2 v = a.tab.tw2[(t & 7) * 16 + k];
         tw1[k] = cf{u.x, u.y};
         tw2[k] = cf{v.x, v.y};
     }
-    for (int i = t; i < GR_N; i += GR_FFT_THREADS) S->code[i] = a.tab.code[(size_t)prn * GR_N + i];
-    for (int i = t; i < (int)(sizeof(GrChan) / 4); i += GR_FFT_THREADS)
+    for (int i = t; i < GR_N; i += NT) S->code[i] = a.tab.code[(size_t)prn * GR_N + i];
+    for (int i = t; i < (int)(sizeof(GrChan) / 4); i += NT)
         reinterpret_cast<uint32_t*>(G)[i] = reinterpret_cast<const uint32_t*>(Gg)[i];
     if (t == 0) {
         if (kStage) {
@@ -589,9 +591,11 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                 const float w32 = (float)(GR_TWO_PI_D * freq);
                 const cf rt = nco_setup(w32, 0.f, n_cyc, t, S);
                 __syncthreads();
-                cf F[16];
-                fold_blocks<IN_FMT, kStage>(F, src, 0, avg, rt, t, S);
-                corr_and_stats<kDense>(F, cs, 1.0f / ((float)avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
+                if (!kWide || t < GR_FFT_THREADS) {
+                    cf F[16];
+                    fold_blocks<IN_FMT, kStage>(F, src, 0, avg, rt, t, S);
+                    corr_and_stats<kDense, kWide>(F, cs, 1.0f / ((float)avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
+                }
                 __syncthreads();
                 z = S->z;
                 if (z > (double)a.cfg.corr_min) {
@@ -644,28 +648,30 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                 u0 = (t + dq) & 255;
                 u1 = u0 ^ 128;
                 E0 = chunk_rot(w32, phase32, u0);
-                E1 = chunk_rot(w32, phase32, u1);
+                if (NC == 2) E1 = chunk_rot(w32, phase32, u1);
                 __syncthreads();
-                cf F[16];
+                float4* ex = reinterpret_cast<float4*>(kDense ? fftbuf : fftbuf + GR_B1_ELEMS);   // free at this point (see fft2048)
                 {
-                    cpk A[16];
+                    cpk A[8 * NC];
                     cf rsum;
-                    fold_blocks_vec(A, rsum, stage, (n_cyc - corr_avg) / 2, corr_avg, u0, u1, S->Rm);
-                    cf G[16];
+                    fold_blocks_vec<NC>(A, rsum, stage, (n_cyc - corr_avg) / 2, corr_avg, u0, u1, S->Rm);
+                    cf G[8 * NC];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
+                    for (int i = 0; i < 8 * NC; ++i) {
                         float ar, ai;
                         cpk_split(A[i], ar, ai);
                         const cf r = cmul(i < 8 ? E0 : E1, S->sigma[i & 7]);
                         G[i] = cmul(affine_sum<IN_FMT>(cf{ar, ai}, rsum), r);
                     }
-                    float4* ex = reinterpret_cast<float4*>(kDense ? fftbuf : fftbuf + GR_B1_ELEMS);   // free at this point (see fft2048)
                     aex_write(ex, u0, G);
-                    aex_write(ex, u1, G + 8);
-                    __syncthreads();
-                    aex_read(ex, t, F);
+                    if (NC == 2) aex_write(ex, u1, G + 8 * (NC - 1));
                 }
-                corr_and_stats<kDense>(F, cs, 1.0f / ((float)corr_avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
+                __syncthreads();
+                if (!kWide || t < GR_FFT_THREADS) {
+                    cf F[16];
+                    aex_read(ex, t, F);
+                    corr_and_stats<kDense, kWide>(F, cs, 1.0f / ((float)corr_avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
+                }
             } else {
                 rt = nco_setup(w32, phase32, n_cyc, t, S);
                 __syncthreads();
@@ -703,15 +709,15 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                     u0 = (t + dq) & 255;
                     u1 = u0 ^ 128;
                     E0 = chunk_rot(w32, phase32, u0);
-                    E1 = chunk_rot(w32, phase32, u1);
+                    if (NC == 2) E1 = chunk_rot(w32, phase32, u1);
                 }
                 const bool wr0 = t + dq >= 256, wr1 = t + dq + 128 >= 256;
-                float qr[16], qi[16];
+                float qr[8 * NC], qi[8 * NC];
                 {
                     cf qall = cf{0.f, 0.f}, qw = cf{0.f, 0.f}, qbs = cf{0.f, 0.f};
                     const cf R1 = S->Rm[2];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < NC; ++h) {
                         const int uh = h ? u1 : u0;
                         const bool wr = h ? wr1 : wr0;
                         cf Eh = h ? E1 : E0;
@@ -740,32 +746,38 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                     }
                 }
                 float2* part2 = reinterpret_cast<float2*>(smem_raw);
-                const int rows_cap = a.buf_bytes / (128 * 8);
+                const int rows_cap = a.buf_bytes / (NT * 8);
                 const int part_rows = rows_cap < n_cyc + 1 ? rows_cap : n_cyc + 1;
                 const unsigned char* p0 = stage + 16 * u0;
                 const unsigned char* p1 = stage + 16 * u1;
                 for (int k0 = 0; k0 <= n_cyc; k0 += part_rows) {
                     const int k1 = (k0 + part_rows <= n_cyc + 1) ? k0 + part_rows : n_cyc + 1;
+#pragma unroll 3
                     for (int k = k0; k < k1; ++k) {
                         const int b0 = k - 1 + (wr0 ? 1 : 0), b1 = k - 1 + (wr1 ? 1 : 0);
                         const bool v0 = (unsigned)b0 < (unsigned)n_cyc, v1 = (unsigned)b1 < (unsigned)n_cyc;
                         cpk x[8], y[8];
                         load8_u8(p0 + (size_t)(v0 ? b0 : 0) * (GR_N * 2), x);
-                        load8_u8(p1 + (size_t)(v1 ? b1 : 0) * (GR_N * 2), y);
-                        // x q = (xr qr - xi qi) + i (xr qi + xi qr): a1 = sum (xr, xi) qr, a2 = sum (xr, xi) qi
-                        cpk a1 = cpk_make(0.f, 0.f), a2 = a1, c1 = a1, c2 = a1;
+                        if (NC == 2) load8_u8(p1 + (size_t)(v1 ? b1 : 0) * (GR_N * 2), y);
+                        // sum x q per chunk: two FFMA2 per sample, two independent chains per chunk (even / odd samples)
+                        cpk a0 = cpk_make(0.f, 0.f), a1 = a0, b0e = a0, b1e = a0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            a1 = cpk_fma(x[i], cpk_bc(qr[i]), a1);
-                            c1 = cpk_fma(y[i], cpk_bc(qr[8 + i]), c1);
-                            a2 = cpk_fma(x[i], cpk_bc(qi[i]), a2);
-                            c2 = cpk_fma(y[i], cpk_bc(qi[8 + i]), c2);
+                        for (int i = 0; i < 8; i += 2) {
+                            a0 = cpk_mac(a0, x[i], qr[i], qi[i]);
+                            b0e = cpk_mac(b0e, x[i + 1], qr[i + 1], qi[i + 1]);
+                            if (NC == 2) {
+                                a1 = cpk_mac(a1, y[i], qr[8 * (NC - 1) + i], qi[8 * (NC - 1) + i]);
+                                b1e = cpk_mac(b1e, y[i + 1], qr[8 * (NC - 1) + i + 1], qi[8 * (NC - 1) + i + 1]);
+                            }
                         }
-                        float a1l, a1h, a2l, a2h, c1l, c1h, c2l, c2h;
-                        cpk_split(a1, a1l, a1h); cpk_split(a2, a2l, a2h); cpk_split(c1, c1l, c1h); cpk_split(c2, c2l, c2h);
-                        const float re = (v0 ? a1l - a2h : 0.f) + (v1 ? c1l - c2h : 0.f);
-                        const float im = (v0 ? a2l + a1h : 0.f) + (v1 ? c2l + c1h : 0.f);
-                        part2[(k - k0) * 128 + t] = make_float2(re, im);
+                        a0 = cpk_add(a0, b0e);
+                        a1 = cpk_add(a1, b1e);
+                        float r0, i0, r1, i1;
+                        cpk_split(a0, r0, i0);
+                        cpk_split(a1, r1, i1);
+                        const float re = (v0 ? r0 : 0.f) + (NC == 2 && v1 ? r1 : 0.f);
+                        const float im = (v0 ? i0 : 0.f) + (NC == 2 && v1 ? i1 : 0.f);
+                        part2[(k - k0) * NT + t] = make_float2(re, im);
                     }
                     __syncthreads();
                     if (k0 == 0 && t <= n_cyc) {                          // B_k: the d & 7 samples in front of the boundary, pass k = t
@@ -785,15 +797,18 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                         S->red[t].z = bsum.x;
                         S->red[t].w = bsum.y;
                     }
-                    if (k0 == 0 && t >= 96 && t < 102)
-                        S->qsum[t - 96] = (S->qred[0][t - 96] + S->qred[1][t - 96]) + (S->qred[2][t - 96] + S->qred[3][t - 96]);
-                    {   // reduce the staged rows: warp w takes rows w, w+4, ...
+                    if (k0 == 0 && t >= 96 && t < 102) {
+                        float qv = (S->qred[0][t - 96] + S->qred[1][t - 96]) + (S->qred[2][t - 96] + S->qred[3][t - 96]);
+                        if (kWide) qv += (S->qred[4][t - 96] + S->qred[5][t - 96]) + (S->qred[6][t - 96] + S->qred[7][t - 96]);
+                        S->qsum[t - 96] = qv;
+                    }
+                    {   // reduce the staged rows: warp w takes rows w, w + NT / 32, ...
                         const int w = t >> 5, l = t & 31;
-                        for (int r = w; r < k1 - k0; r += 4) {
-                            float2 v = part2[r * 128 + l];
+                        for (int r = w; r < k1 - k0; r += NT / 32) {
+                            float2 v = part2[r * NT + l];
 #pragma unroll
-                            for (int m = 1; m < 4; ++m) {
-                                const float2 u = part2[r * 128 + l + 32 * m];
+                            for (int m = 1; m < NT / 32; ++m) {
+                                const float2 u = part2[r * NT + l + 32 * m];
                                 v.x += u.x; v.y += u.y;
                             }
                             v.x = warp_sum(v.x); v.y = warp_sum(v.y);
@@ -1076,7 +1091,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                     O->max_corr = S->z;
                     O->reserved[0] = 0; O->reserved[1] = 0;
                 }
-            } else {
+            } else if (wid == 0) {
                 // ---- carrier loop: phaseLockedLoop, gpslib.py:1215-1262 ----
                 float ph[2];
 #pragma unroll
@@ -1233,13 +1248,13 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, kDense ? 3 : 1) track_kernel(c
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         } else {
-            for (int i = t; i < (int)(sizeof(gr_epoch_out) / 4); i += GR_FFT_THREADS)
+            for (int i = t; i < (int)(sizeof(gr_epoch_out) / 4); i += NT)
                 reinterpret_cast<uint32_t*>(gO)[i] = reinterpret_cast<const uint32_t*>(O)[i];
         }
     }
     if (t == 0 && a.out_tma) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncthreads();
-    for (int i = t; i < (int)(sizeof(GrChan) / 4); i += GR_FFT_THREADS)
+    for (int i = t; i < (int)(sizeof(GrChan) / 4); i += NT)
         reinterpret_cast<uint32_t*>(Gg)[i] = reinterpret_cast<const uint32_t*>(G)[i];
 }
 
@@ -1297,6 +1312,8 @@ extern "C" int gr_track_bank_create(const gr_track_cfg* cfg, gr_track_bank** ban
     GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(track_smem_bytes() + track_stage_bytes(GR_MAX_NCYC))));
     GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(track_smem_bytes() + track_stage_bytes(GR_MAX_NCYC))));
+    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(track_smem_bytes() + track_stage_bytes(GR_MAX_NCYC))));
     gr_lib()->live_handles += 1;
     *bank = b;
@@ -1441,16 +1458,27 @@ extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int
     a.stage = b->cfg.in_format == GR_IN_U8IQ && ((uintptr_t)d_samples % 16) == 0 && ((2 * rec_stride) % 16) == 0;
     a.buf_bytes = GR_TRACK_BUF_BYTES;
     a.part_rows = GR_PART_ROWS;
-    // dense form when the launch has more channels than fit at two CTAs per SM and the epoch is short enough for three
-    const char* dense_env = getenv("GPSB200_TRACK_DENSE");          // development / test switch: 0 = never, 1 = whenever it fits (a getenv per launch, ~50 ns: the tests flip it between banks)
+    // Form of the kernel.  wide (256 threads per channel): launches that leave SMs to spare anyway (at most one CTA per SM);
+    // dense (three CTAs per SM): more channels than fit at two CTAs per SM, epoch short enough for three; else standard.
+    // GPSB200_TRACK_FORM = std | dense | wide and GPSB200_TRACK_DENSE = 0 | 1 are development / test switches (a getenv per
+    // launch, ~50 ns: the tests flip them between banks).
+    const char* form_env = getenv("GPSB200_TRACK_FORM");
+    const char* dense_env = getenv("GPSB200_TRACK_DENSE");
     const size_t dense_smem = track_smem_bytes(track_dense_buf_bytes(b->cfg.n_cyc)) + track_stage_bytes(b->cfg.n_cyc);
-    const bool dense = a.stage && 3 * (dense_smem + 1024) <= 227 * 1024 &&
-                       (dense_env ? atoi(dense_env) != 0 : a.n_active > 2 * gr_lib()->num_sms);
+    const bool dense_fits = a.stage && 3 * (dense_smem + 1024) <= 227 * 1024;
+    bool dense = dense_fits && (dense_env ? atoi(dense_env) != 0 : a.n_active > 2 * gr_lib()->num_sms);
+    bool wide = a.stage && !dense && !dense_env && a.n_active <= gr_lib()->num_sms;
+    if (form_env) {
+        dense = dense_fits && !strcmp(form_env, "dense");
+        wide = a.stage && !strcmp(form_env, "wide");
+    }
     if (dense) {
         a.buf_bytes = (int)track_dense_buf_bytes(b->cfg.n_cyc);
         a.part_rows = track_dense_rows(b->cfg.n_cyc);
         track_kernel<GR_IN_U8IQ, true, true><<<a.n_active, GR_FFT_THREADS, dense_smem, s>>>(a);
-    } else if (a.stage)
+    } else if (wide)
+        track_kernel<GR_IN_U8IQ, true, false, 256><<<a.n_active, 256, track_smem_bytes() + track_stage_bytes(b->cfg.n_cyc), s>>>(a);
+    else if (a.stage)
         track_kernel<GR_IN_U8IQ, true><<<a.n_active, GR_FFT_THREADS, track_smem_bytes() + track_stage_bytes(b->cfg.n_cyc), s>>>(a);
     else if (b->cfg.in_format == GR_IN_U8IQ)
         track_kernel<GR_IN_U8IQ, false><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);

@@ -345,3 +345,36 @@ def test_corrlst_fifo_past_60_s_at_ncyc8_and_quality_triggered_sweep(gpu):
     assert np.array_equal(recs["corr_l"], cl)
     assert np.array_equal(recs["sweep"].astype(bool), sw), np.nonzero(recs["sweep"].astype(bool) != sw)[0][:5]
     assert sw[first + 1] or recs["tracked"][first + 1] == 0
+
+
+def test_wide_form_agrees_with_standard_form(gpu, monkeypatch):
+    """The 256-thread form (small launches: one CTA per SM at most) runs the two sample passes with one 8-sample chunk per
+    thread instead of two; the transforms, the loop filter and every decision are the same code on the first 128 threads.
+    Correlation values are bit-identical (the same per-chunk arithmetic), prompt sums differ in the order of their last
+    additions: decisions exact, values within 2e-5."""
+    import torch
+    from gps_sdr_receiver_b200 import synth
+    from gps_sdr_receiver_b200.tracking import TrackBank
+    n_cyc, ngps, n_ep = 8, 8 * 2048, 400
+    sats = [synth.Sat(prn=4, doppler=1210.0, delay=100.3, amp=0.08, bit_offset_ms=3, bit_seed=5),
+            synth.Sat(prn=19, doppler=-3390.0, delay=1999.7, amp=0.08, bit_offset_ms=11, bit_seed=6),
+            synth.Sat(prn=31, doppler=40.0, delay=1023.5, amp=0.06, bit_offset_ms=0, bit_seed=7)]
+    raw = torch.from_numpy(synth.make_iq(sats, n_ep * n_cyc, seed=5)).cuda()
+    out = {}
+    for form in ("std", "wide"):
+        monkeypatch.setenv("GPSB200_TRACK_FORM", form)
+        bank = TrackBank(n_cyc, 4)
+        for s in sats:
+            bank.add(s.prn, 50.0 * round(s.doppler / 50.0), (int(s.delay) + 1) % 2048)
+        out[form] = TrackBank.records_from_tensor(bank.process_dev(raw, ngps, n_ep)).copy()
+        torch.cuda.synchronize()
+        bank.close()
+    monkeypatch.delenv("GPSB200_TRACK_FORM")
+    a, b = out["std"], out["wide"]
+    for f in ("delay", "corr_delay", "locked", "sweep", "ms_time", "n_prompt", "n_prev", "edge_mask", "edge_len", "edge0", "corr_q", "corr_l"):
+        assert np.array_equal(a[f], b[f]), f
+    for f in ("max_corr", "corr3", "corr_mean", "corr_std"):                 # FREQ may sit one float32 ulp apart for a while (the last
+        np.testing.assert_allclose(a[f], b[f], rtol=2e-5, err_msg=f)         # additions of the prompt sums differ): 1e-5-level echoes
+    np.testing.assert_allclose(a["freq"], b["freq"], rtol=1e-6)
+    np.testing.assert_allclose(a["prompt"], b["prompt"], rtol=0, atol=1e-4 * np.abs(a["prompt"]).max())
+    assert b["locked"][-1].all()
