@@ -74,6 +74,7 @@ SIGNATURES = {
     "gr_acq_classify_bins": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "gr_acq_plan_create": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "gr_acq_plan_destroy": (C.c_int, [_P]),
+    "gr_acq_plan_form": (C.c_int, [_P]),
     "gr_acq_run_dev": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P]),
     "gr_acq_run_host": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P]),
     "gr_acq_last_launches": (C.c_int, [_P]),

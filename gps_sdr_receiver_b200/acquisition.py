@@ -52,6 +52,12 @@ class AcqPlan:
         self._h = h
 
     @property
+    def form(self) -> str:
+        """'fast' (shared spectra, block rotations) or 'exact' (the reference's float32 phase argument for every sample
+        of every bin): chosen by gr_acq_plan_create from the grid's largest phase argument (include/gps_b200.h)."""
+        return "exact" if _capi.lib().gr_acq_plan_form(self._h) else "fast"
+
+    @property
     def cells_per_recording(self) -> int:
         return len(self.prns) * len(self.bin_hz) * glob.CODE_SAMPLES
 

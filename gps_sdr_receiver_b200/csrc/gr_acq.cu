@@ -66,6 +66,7 @@ struct AcqArgs {
     int nrec, nprn, nbins, nbase, ngroups, tcoh, nnoncoh, mode;
     int nchunks, bins_per_chunk;   // forward kernel: base bins per CTA
     int exact_nco;                 // per-sample float32 phase arguments also for tcoh > 1 (see acq_fwd_kernel)
+    int need_e1;                   // some bin has an odd shift: the forward kernel writes the second (one-bin shifted) copy too
     float scale;               // 1 / (tcoh * 2048)
     // PRN list and (base << 16 | shift) per bin in the kernel parameters when they fit: the inverse kernel looks them up
     // at job boundaries, where a global load would be an exposed L2 round trip (in_params = 0: use the arrays above)
@@ -101,6 +102,15 @@ __device__ __forceinline__ float nco_arg(float w32, long long n) {
     const float tsec = __fdiv_rn((float)(n + 1), GR_FS);
     return __fmul_rn(w32, tsec);
 }
+// fl32(k / fs) for an integer-valued float k < 2^23 in three instructions: quotient estimate, exact remainder, one
+// correction.  Equal to the correctly rounded IEEE division for every k = 1 .. 2^23 (checked exhaustively on the host);
+// the generic division is ~10 instructions with a slow-path branch, and the exact-NCO forward kernel runs one per sample.
+__device__ __forceinline__ float tsec_of(float k) {
+    const float y = 1.0f / GR_FS;
+    const float q0 = __fmul_rn(k, y);
+    const float r = __fmaf_rn(-q0, GR_FS, k);
+    return __fmaf_rn(r, y, q0);
+}
 
 // ---- kernel 1: forward spectra ------------------------------------------------------------------
 // CTA = (recording, non-coherent interval, chunk of base bins); it loops over its bins with the FFT
@@ -115,6 +125,15 @@ __device__ __forceinline__ cf nco_fast(float arg) {            // exp(-i arg)
     const float k = rintf(arg * 0.15915494309189535f);
     float r = fmaf(k, -6.28125f, arg);                         // 6.28125 = 201/32: k * C1 is exact
     r = fmaf(k, -1.9353071795864769e-3f, r);                   // 2 pi - 6.28125
+    return cf{__cosf(r), -__sinf(r)};
+}
+
+// the same with the rounding to a whole number of turns done by the 1.5 * 2^23 trick (two full-rate additions instead of
+// the quarter-rate FRND): the sample loop of the reference-exact form runs one of these per sample and bin
+__device__ __forceinline__ cf nco_fast2(float arg) {           // exp(-i arg), |arg| < 2^22 turns
+    const float k = __fadd_rn(fmaf(arg, 0.15915494309189535f, 12582912.0f), -12582912.0f);
+    float r = fmaf(k, -6.28125f, arg);
+    r = fmaf(k, -1.9353071795864769e-3f, r);
     return cf{__cosf(r), -__sinf(r)};
 }
 
@@ -153,9 +172,11 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
         }
     }
     cf* Rtab = smem + GR_B1_ELEMS + GR_B2_ELEMS;                    // [tcoh] block rotations of the current bin (multi-block form)
-    for (int bin = bin0; bin < bin1; ++bin) {
+    const int bin_step = (!kOneBlock && a.exact_nco) ? 2 : 1;
+    for (int bin = bin0; bin < bin1; bin += bin_step) {
         const float w32 = a.w32[bin];
         cf X[16];
+        cf Y[(kOneBlock ? 1 : 16)];                                 // second bin of the pair (exact form only)
         if (kOneBlock) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -169,19 +190,26 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
             // rounding of the reference's per-sample phase argument, up to 3e-5 rad, is then not reproduced sample by
             // sample; the effect on the correlation is below 1e-6 relative.)
             if (a.exact_nco) {
-                // reference-exact form (GPSB200_ACQ_EXACT_NCO): every sample of every block gets the reference's own float32
-                // argument fl32(w32 * fl32((n + 1) / fs)), tcoh x more sin / cos.  For searches whose |w t| is so large
-                // (10 kHz x 200 ms = 1.2e4 rad, ulp 1e-3 rad) that the reference's rounding noise exceeds the 1e-4 tolerance.
+                // reference-exact form: every sample of every block gets the reference's own float32 argument
+                // fl32(w32 * fl32((n + 1) / fs)), tcoh x more sin / cos.  For searches whose |w t| is so large (10 kHz x 200 ms
+                // = 1.2e4 rad, ulp 1e-3 rad) that the reference's rounding noise exceeds the 1e-4 tolerance.  Two bins at a time:
+                // the sample load, its conversion and its time value are shared by both.
+                const bool two = bin + 1 < bin1;
+                const float w32b = two ? a.w32[bin + 1] : w32;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) X[j] = cf{0.f, 0.f};
-                for (int i = 0; i < a.tcoh; ++i) {
+                for (int j = 0; j < 16; ++j) { X[j] = cf{0.f, 0.f}; Y[j] = cf{0.f, 0.f}; }
+                float fn0 = (float)(base0 + 1);                    // n + 1 of this thread's first sample of block i (exact: < 2^24)
+                for (int i = 0; i < a.tcoh; ++i, fn0 += (float)GR_N) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const long long n = base0 + (long long)i * GR_N + 128 * j;
-                        const cf x = load_sample<IN_FMT>(src, n);
-                        const cf e = nco_fast(nco_arg(w32, n));
-                        X[j].x += x.x * e.x - x.y * e.y;
-                        X[j].y += x.y * e.x + x.x * e.y;
+                        const cf x = load_sample<IN_FMT>(src, base0 + (long long)i * GR_N + 128 * j);
+                        const float ts = tsec_of(fn0 + (float)(128 * j));
+                        const cf e = nco_fast2(__fmul_rn(w32, ts));
+                        const cf f = nco_fast2(__fmul_rn(w32b, ts));
+                        X[j].x = fmaf(x.x, e.x, X[j].x); X[j].x = fmaf(-x.y, e.y, X[j].x);
+                        X[j].y = fmaf(x.y, e.x, X[j].y); X[j].y = fmaf(x.x, e.y, X[j].y);
+                        Y[j].x = fmaf(x.x, f.x, Y[j].x); Y[j].x = fmaf(-x.y, f.y, Y[j].x);
+                        Y[j].y = fmaf(x.y, f.x, Y[j].y); Y[j].y = fmaf(x.x, f.y, Y[j].y);
                     }
                 }
             } else {
@@ -205,17 +233,22 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
             for (int j = 0; j < 16; ++j) X[j] = cmul(X[j], nco_fast(nco_arg(w32, base0 + 128 * j)));
             }
         }
-        fft2048<true>(X, smem, tw1, tw2, t);
         // two copies in natural order, E0[m] = X[m] and E1[m] = X[m + 1]: the inverse kernel fetches a spectrum rotated by
-        // any number of bins with 16-byte aligned bulk copies (even rotations of E0, odd ones as even rotations of E1)
-        float2* e0 = a.spec + ((size_t)(rec * a.nbase + bin) * a.nnoncoh + k) * (2 * GR_N);
+        // any number of bins with 16-byte aligned bulk copies (even rotations of E0, odd ones as even rotations of E1; the
+        // second copy is skipped when no bin of the plan has an odd shift)
+        auto emit = [&](cf* V, int b) {
+            fft2048<true>(V, smem, tw1, tw2, t);
+            float2* e0 = a.spec + ((size_t)(rec * a.nbase + b) * a.nnoncoh + k) * (2 * GR_N);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float2 v = make_float2(X[j].x, X[j].y);
-            e0[t + 128 * j] = v;
-            e0[GR_N + ((t + 128 * j + GR_N - 1) & (GR_N - 1))] = v;
-        }
-        __syncthreads();                                           // the FFT buffers (and Rtab) are reused by the next bin
+            for (int j = 0; j < 16; ++j) {
+                const float2 v = make_float2(V[j].x, V[j].y);
+                e0[t + 128 * j] = v;
+                if (a.need_e1) e0[GR_N + ((t + 128 * j + GR_N - 1) & (GR_N - 1))] = v;
+            }
+            __syncthreads();                                       // the FFT buffers (and Rtab) are reused by the next bin
+        };
+        emit(X, bin);
+        if (!kOneBlock && a.exact_nco && bin + 1 < bin1) emit(Y, bin + 1);
     }
 }
 
@@ -778,7 +811,18 @@ extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* b
     p->pipe_ready = false;
     std::vector<int32_t> bin_base(nbins), bin_shift(nbins);
     std::vector<double> base_f(nbins);
-    p->exact_nco = getenv("GPSB200_ACQ_EXACT_NCO") != nullptr;      // implies one spectrum per bin (the reference's w32 per bin)
+    // Form of the forward kernel.  The reference evaluates one float32 phase argument fl32(w32 * fl32((n+1)/fs)) per sample
+    // and bin (gpsrecv.py:232-235); its rounding error grows with |w| T.  While that error stays far below the 1e-4
+    // tolerance the fast form (one spectrum per 1-kHz class, block rotations) is indistinguishable from it; beyond --
+    // largest argument x 2^-24 above 1e-4 rad, e.g. +-10 kHz over 200 ms: 7.5e-4 rad -- the plan reproduces the
+    // reference's argument sample by sample and bin by bin ("exact" form).  GPSB200_ACQ_EXACT_NCO=1 / =0 force a form.
+    {
+        double fmax = 0.0;
+        for (int b = 0; b < nbins; ++b) fmax = fmax > fabs(bin_hz[b]) ? fmax : fabs(bin_hz[b]);
+        const double argmax = 2.0 * 3.141592653589793 * fmax * (double)tcoh_ms * (double)nnoncoh * 1e-3;
+        const char* e = getenv("GPSB200_ACQ_EXACT_NCO");
+        p->exact_nco = e ? (atoi(e) != 0) : (argmax * 5.9604644775390625e-8 > 1e-4);
+    }
     const int nb = gr_acq_classify_bins(bin_hz, nbins, getenv("GPSB200_ACQ_NOSHARE") == nullptr && !p->exact_nco, bin_base.data(),
                                         bin_shift.data(), base_f.data());
     if (nb < 0) { delete p; return nb; }
@@ -830,6 +874,7 @@ extern "C" int gr_acq_plan_destroy(gr_acq_plan* p) {
 }
 
 extern "C" int gr_acq_last_launches(const gr_acq_plan* p) { return p ? p->last_launches : 0; }
+extern "C" int gr_acq_plan_form(const gr_acq_plan* p) { return p && p->exact_nco ? GR_ACQ_FORM_EXACT : GR_ACQ_FORM_FAST; }
 
 static int grow(void** ptr, size_t* have, size_t need) {
     if (need <= *have) return GR_OK;
@@ -890,6 +935,8 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         a.bin_shift = p->d_bin_shift;
         a.nbase = p->nbase;
         a.exact_nco = p->exact_nco;
+        a.need_e1 = 0;
+        for (int b = 0; b < p->nbins; ++b) a.need_e1 |= p->h_bin_code[b] & 1;
         a.nrec = nr;
         a.nprn = p->nprn;
         a.nbins = p->nbins;

@@ -79,10 +79,16 @@ typedef struct gr_acq_plan gr_acq_plan;
  * reference's float32 time base t[n] = (n+1)/fs (gpsrecv.py:32-33, 232-235).
  * Bins that differ by a multiple of fs/2048 = 1 kHz share one forward FFT (their spectra
  * are circular shifts of each other); a cell's value does not depend on which other
- * bins the plan holds.  |bin_hz| must stay below fs/2.  Environment (read at creation):
- * GPSB200_ACQ_NOSHARE=1 one forward FFT per bin, as the reference computes it;
- * GPSB200_ACQ_EXACT_NCO=1 additionally the reference's float32 phase argument for every
- * sample also when tcoh_ms > 1 (slower forward kernel; for searches with |2 pi f t| ~ 1e4). */
+ * bins the plan holds.  |bin_hz| must stay below fs/2.
+ * Form of the forward kernel (gr_acq_plan_form): the reference's float32 phase argument
+ * fl32(w32 * fl32((n+1)/fs)) carries a rounding error that grows with |f| T.  Searches where it
+ * stays far below the 1e-4 tolerance (largest argument x 2^-24 <= 1e-4 rad: e.g. +-10 kHz over
+ * 10 ms) run in the FAST form (shared spectra, block rotations); longer / wider searches (e.g.
+ * +-10 kHz over 200 ms) run in the EXACT form, which reproduces the reference's argument for
+ * every sample of every bin.  Environment (read at creation): GPSB200_ACQ_EXACT_NCO=1 / =0
+ * forces the exact / fast form; GPSB200_ACQ_NOSHARE=1 one forward FFT per bin in the fast form. */
+#define GR_ACQ_FORM_FAST 0
+#define GR_ACQ_FORM_EXACT 1
 /* The classification gr_acq_plan_create applies to its Doppler bins (host only, needs no GPU): base[b] = index of the
  * forward spectrum bin b uses, shift[b] = its circular shift in FFT bins (0..2047), base_hz[i] = frequency the i-th base
  * spectrum is computed for (in [-500, 500) Hz when sharing is on).  Returns the number of base spectra or a negative
@@ -91,6 +97,8 @@ int gr_acq_classify_bins(const double* bin_hz, int nbins, int share, int32_t* ba
 int gr_acq_plan_create(const int32_t* prns, int nprn, const double* bin_hz, int nbins,
                        int tcoh_ms, int nnoncoh, int mode, int in_format, gr_acq_plan** plan);
 int gr_acq_plan_destroy(gr_acq_plan* plan);
+/* GR_ACQ_FORM_FAST or GR_ACQ_FORM_EXACT: which form gr_acq_plan_create chose for this grid */
+int gr_acq_plan_form(const gr_acq_plan* plan);
 /* nrec independent recordings, `rec_stride` samples apart; d_out[nrec][nprn][nbins]. */
 int gr_acq_run_dev(gr_acq_plan* plan, const void* d_samples, int nrec, int64_t rec_stride,
                    gr_acq_cell* d_out, void* stream);
