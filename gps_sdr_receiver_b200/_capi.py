@@ -94,6 +94,7 @@ SIGNATURES = {
     "gr_track_process_host": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int64, _P]),
     "gr_track_num_active": (C.c_int, [_P]),
     "gr_track_last_launches": (C.c_int, [_P]),
+    "gr_track_bank_form": (C.c_int, [_P]),
     "gr_debug_fft2048": (C.c_int, [_P, _P, C.c_int, C.c_int]),
 }
 

@@ -102,16 +102,6 @@ __device__ __forceinline__ float nco_arg(float w32, long long n) {
     const float tsec = __fdiv_rn((float)(n + 1), GR_FS);
     return __fmul_rn(w32, tsec);
 }
-// fl32(k / fs) for an integer-valued float k < 2^23 in three instructions: quotient estimate, exact remainder, one
-// correction.  Equal to the correctly rounded IEEE division for every k = 1 .. 2^23 (checked exhaustively on the host);
-// the generic division is ~10 instructions with a slow-path branch, and the exact-NCO forward kernel runs one per sample.
-__device__ __forceinline__ float tsec_of(float k) {
-    const float y = 1.0f / GR_FS;
-    const float q0 = __fmul_rn(k, y);
-    const float r = __fmaf_rn(-q0, GR_FS, k);
-    return __fmaf_rn(r, y, q0);
-}
-
 // ---- kernel 1: forward spectra ------------------------------------------------------------------
 // CTA = (recording, non-coherent interval, chunk of base bins); it loops over its bins with the FFT
 // twiddles (and, for tcoh = 1, the 16 samples per thread) held in registers: wipe-off, time-domain fold of
@@ -125,15 +115,6 @@ __device__ __forceinline__ cf nco_fast(float arg) {            // exp(-i arg)
     const float k = rintf(arg * 0.15915494309189535f);
     float r = fmaf(k, -6.28125f, arg);                         // 6.28125 = 201/32: k * C1 is exact
     r = fmaf(k, -1.9353071795864769e-3f, r);                   // 2 pi - 6.28125
-    return cf{__cosf(r), -__sinf(r)};
-}
-
-// the same with the rounding to a whole number of turns done by the 1.5 * 2^23 trick (two full-rate additions instead of
-// the quarter-rate FRND): the sample loop of the reference-exact form runs one of these per sample and bin
-__device__ __forceinline__ cf nco_fast2(float arg) {           // exp(-i arg), |arg| < 2^22 turns
-    const float k = __fadd_rn(fmaf(arg, 0.15915494309189535f, 12582912.0f), -12582912.0f);
-    float r = fmaf(k, -6.28125f, arg);
-    r = fmaf(k, -1.9353071795864769e-3f, r);
     return cf{__cosf(r), -__sinf(r)};
 }
 

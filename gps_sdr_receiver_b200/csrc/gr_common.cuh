@@ -29,3 +29,32 @@ struct GrTables {
     const float2* tw2;       // [8][16]    W_128^(n3*k)    forward
     const int8_t* chips;     // [GR_MAX_PRN+1][1024] the 1023 Gold-code chips (+1/-1), padded
 };
+
+#if defined(__CUDACC__)
+// ---- the reference's NCO, sample by sample ------------------------------------------------------------------------
+// The reference rotates sample n by exp(-i fl32(phase + fl32(w32 * t_n))), t_n = fl32((n + 1) / fs) (gpsrecv.py:32-33,
+// 232-235; gpslib.py:1053-1054, 1343-1346).  At |w t| ~ 1e3 .. 1e4 rad the float32 rounding of that argument (6e-5 .. 1e-3
+// rad) is the largest term in the distance between the reference and the mathematically exact rotation, so the forms
+// of the kernels that have to stay within 1e-4 of the reference evaluate the same argument per sample.
+// fl32(k / fs) for an integer-valued float k < 2^23 in three instructions: quotient estimate, exact remainder, one
+// correction.  Equal to the correctly rounded IEEE division for every k = 1 .. 2^23 (checked exhaustively on the host);
+// the generic division is ~10 instructions with a slow-path branch.
+__device__ __forceinline__ float tsec_of(float k) {
+    const float y = 1.0f / GR_FS;
+    const float q0 = __fmul_rn(k, y);
+    const float r = __fmaf_rn(-q0, GR_FS, k);
+    return __fmaf_rn(r, y, q0);
+}
+// exp(-i arg), |arg| < 2^22 turns: 2-constant Cody-Waite reduction (6.28125 = 201/32: k * C1 is exact) + MUFU sin / cos,
+// |err| < 5e-7; the rounding to a whole number of turns by the 1.5 * 2^23 trick (two full-rate additions, no FRND)
+__device__ __forceinline__ cf nco_fast2(float arg) {
+    const float k = __fadd_rn(fmaf(arg, 0.15915494309189535f, 12582912.0f), -12582912.0f);
+    float r = fmaf(k, -6.28125f, arg);
+    r = fmaf(k, -1.9353071795864769e-3f, r);
+    return cf{__cosf(r), -__sinf(r)};
+}
+// the reference's factor for sample n of a wipe-off with carried phase `phase32`; fn1 = (float)(n + 1)
+__device__ __forceinline__ cf nco_exact(float w32, float phase32, float fn1) {
+    return nco_fast2(__fadd_rn(phase32, __fmul_rn(w32, tsec_of(fn1))));
+}
+#endif

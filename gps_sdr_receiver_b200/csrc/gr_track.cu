@@ -82,6 +82,7 @@ struct gr_track_bank {
     void* d_in;  size_t in_bytes;
     gr_epoch_out* d_out; size_t out_bytes;
     int last_launches;
+    int exact_nco;                   // the reference's float32 phase argument per sample (default) | factorised NCO (GPSB200_TRK_FAST_NCO=1)
     bool pipe_ready;                 // streams/events of the host pipeline
     cudaStream_t s_in, s_out;
     cudaEvent_t ev_in[2], ev_run[2], ev_out[2];
@@ -360,6 +361,61 @@ __device__ __forceinline__ void fold_blocks_vec(cpk* A, cf& rsum, const unsigned
         }
     }
 }
+// ---- reference-exact NCO (kExact): one float32 phase argument per sample, as the reference evaluates it -----------------
+// exp(-i fl32(PHASE + fl32(w * SEC_TIME[n]))) (gpslib.py:1343-1346).  At 5 kHz x 32 ms the argument reaches 1000 rad, where
+// one float32 ulp is 6e-5 rad: the factorised NCO above computes the mathematically exact rotation instead and is that far
+// from the reference on every sample (oracle/parity_floor.py: FREQ bit-equal on half the epochs only, complex prompts 4e-4
+// apart).  This form reproduces the argument itself (sin / cos of it to 5e-7) and pays N_CYC x 2048 x 2 sin / cos per epoch
+// and channel instead of 2 per thread.
+// reader's conversion, gpsrecv.py:168-173: complex64(raw) / 127.5 - (1 + 1j): two float32 roundings per component
+__device__ __forceinline__ cpk true_sample_pk(cpk b) {
+    return cpk_add(cpk_mul(b, cpk_make(1.0f / 127.5f, 1.0f / 127.5f)), cpk_make(-1.f, -1.f));
+}
+template <int IN_FMT, bool kStage>
+__device__ __forceinline__ cf load_true(const void* base, long long n) {
+    const cf v = load_raw<IN_FMT, kStage>(base, n);
+    if (IN_FMT == GR_IN_U8IQ) return cf{__fsub_rn(__fmul_rn(v.x, 1.0f / 127.5f), 1.0f), __fsub_rn(__fmul_rn(v.y, 1.0f / 127.5f), 1.0f)};
+    return v;
+}
+// F[j] = sum_b x_b[t + 128 j] e(2048 b + t + 128 j)   (natural FFT layout; no affine map, no rotation left to apply)
+template <int IN_FMT, bool kStage>
+__device__ __forceinline__ void fold_blocks_exact(cf* F, const void* src, int first, int nblk, float w32, float phase32, int t) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) F[j] = cf{0.f, 0.f};
+    for (int b = first; b < first + nblk; ++b) {
+        const int base = b * GR_N + t;
+        const float f0 = (float)(base + 1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const cf x = load_true<IN_FMT, kStage>(src, base + 128 * j);
+            const cf e = nco_exact(w32, phase32, f0 + (float)(128 * j));
+            F[j].x = fmaf(x.x, e.x, F[j].x); F[j].x = fmaf(-x.y, e.y, F[j].x);
+            F[j].y = fmaf(x.x, e.y, F[j].y); F[j].y = fmaf(x.y, e.x, F[j].y);
+        }
+    }
+}
+// vector form: A[8 h + i] = sum_b x_b[8 u_h + i] e(2048 b + 8 u_h + i)
+template <int NC>
+__device__ __forceinline__ void fold_blocks_vec_exact(cpk* A, const unsigned char* stage, int first, int nblk, int u0, int u1,
+                                                      float w32, float phase32) {
+#pragma unroll
+    for (int i = 0; i < 8 * NC; ++i) A[i] = cpk_make(0.f, 0.f);
+    for (int b = first; b < first + nblk; ++b) {
+        const unsigned char* pb = stage + (size_t)b * (GR_N * 2);
+#pragma unroll
+        for (int h = 0; h < NC; ++h) {
+            const int u = h ? u1 : u0;
+            cpk x[8];
+            load8_u8(pb + 16 * u, x);
+            const float f0 = (float)(b * GR_N + 8 * u + 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const cf e = nco_exact(w32, phase32, f0 + (float)i);
+                A[8 * h + i] = cpk_mac(A[8 * h + i], true_sample_pk(x[i]), e.x, e.y);
+            }
+        }
+    }
+}
 // Exchange "thread owns chunks" -> "thread t owns elements t + 128 j" (the FFT's input layout) through 16 KiB of shared
 // memory: chunk u = 64 bytes, its four 16-byte quarters swizzled by (u >> 1) & 3 so that the 128-bit stores of a
 // quarter-warp and the 64-bit loads of a half-warp are conflict-free (checked exhaustively on the host, all rotations).
@@ -491,7 +547,8 @@ __device__ __forceinline__ void trk_stage_issue(void* dst, const char* gsrc, uns
 // not bandwidth, is what the epoch time is made of.
 // NT = 256 ("wide" form, launches of at most one CTA per SM): the two sample passes run on 256 threads with one chunk per
 // thread and block; the transforms and everything serial stay on the first 128 threads (named barrier 1).
-template <int IN_FMT, bool kStage, bool kDense = false, int NT = GR_FFT_THREADS>
+// kExact: the reference's float32 phase argument for every sample (see nco_exact) instead of the factorised NCO.
+template <int IN_FMT, bool kStage, bool kDense = false, int NT = GR_FFT_THREADS, bool kExact = false>
 __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* fftbuf = reinterpret_cast<cf*>(smem_raw);
@@ -589,11 +646,13 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
             int j = 0;
             while (delay < 0 && j < a.cfg.it_sweep) {
                 const float w32 = (float)(GR_TWO_PI_D * freq);
-                const cf rt = nco_setup(w32, 0.f, n_cyc, t, S);
+                cf rt = cf{0.f, 0.f};
+                if (!kExact) rt = nco_setup(w32, 0.f, n_cyc, t, S);
                 __syncthreads();
                 if (!kWide || t < GR_FFT_THREADS) {
                     cf F[16];
-                    fold_blocks<IN_FMT, kStage>(F, src, 0, avg, rt, t, S);
+                    if (kExact) fold_blocks_exact<IN_FMT, kStage>(F, src, 0, avg, w32, 0.f, t);   // getCorrMax: phase = 0
+                    else fold_blocks<IN_FMT, kStage>(F, src, 0, avg, rt, t, S);
                     corr_and_stats<kDense, kWide>(F, cs, 1.0f / ((float)avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
                 }
                 __syncthreads();
@@ -642,26 +701,115 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
             cf rt = cf{0.f, 0.f};
             int dq = 0, u0 = 0, u1 = 0;
             cf E0 = cf{0.f, 0.f}, E1 = cf{0.f, 0.f};
+            const int d_spec = C->delay;                     // DELAY going into the epoch (thread 0 updates it behind the next barriers)
             if constexpr (kVec) {
-                nco_setup_vec(w32, n_cyc, t, S);
+                if (!kExact) nco_setup_vec(w32, n_cyc, t, S);
                 dq = S->dq;
                 u0 = (t + dq) & 255;
                 u1 = u0 ^ 128;
-                E0 = chunk_rot(w32, phase32, u0);
-                if (NC == 2) E1 = chunk_rot(w32, phase32, u1);
+                if (!kExact) {
+                    E0 = chunk_rot(w32, phase32, u0);
+                    if (NC == 2) E1 = chunk_rot(w32, phase32, u1);
+                }
                 __syncthreads();
                 float4* ex = reinterpret_cast<float4*>(kDense ? fftbuf : fftbuf + GR_B1_ELEMS);   // free at this point (see fft2048)
                 {
                     cpk A[8 * NC];
-                    cf rsum;
-                    fold_blocks_vec<NC>(A, rsum, stage, (n_cyc - corr_avg) / 2, corr_avg, u0, u1, S->Rm);
                     cf G[8 * NC];
+                    if constexpr (kExact) {
+                        // ONE pass over the epoch's samples: every sample is rotated once, y = x e(n), and goes into the coherent
+                        // fold (blocks first .. first + corr_avg - 1) AND into the prompt sums, the latter formed for the DELAY the
+                        // epoch started with.  The correlation below changes DELAY on a few per cent of the epochs only; then
+                        // the prompt sums are formed again for the new DELAY (the two-pass code further down).
+                        const int first = (n_cyc - corr_avg) / 2;
+                        const int r8s = d_spec & 7;
+                        const bool wr0 = t + dq >= 256, wr1 = t + dq + 128 >= 256;
+                        float cc[8 * NC];
 #pragma unroll
-                    for (int i = 0; i < 8 * NC; ++i) {
-                        float ar, ai;
-                        cpk_split(A[i], ar, ai);
-                        const cf r = cmul(i < 8 ? E0 : E1, S->sigma[i & 7]);
-                        G[i] = cmul(affine_sum<IN_FMT>(cf{ar, ai}, rsum), r);
+                        for (int h = 0; h < NC; ++h) {
+                            const int uh = h ? u1 : u0;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                cc[8 * h + i] = S->code[(8 * uh + i - d_spec) & (GR_N - 1)];
+                                if (h == 0 && t == 0) S->qb[i] = cf{i < r8s ? cc[i] : 0.f, 0.f};
+                            }
+                        }
+                        float2* part2 = reinterpret_cast<float2*>(smem_raw);       // row k = pass k, this thread's column only
+                        for (int k = 0; k <= n_cyc; ++k) part2[k * NT + t] = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int i = 0; i < 8 * NC; ++i) A[i] = cpk_make(0.f, 0.f);
+                        for (int b = 0; b < n_cyc; ++b) {
+                            const bool fold_on = b >= first && b < first + corr_avg;
+                            const unsigned char* pb = stage + (size_t)b * (GR_N * 2);
+#pragma unroll
+                            for (int h = 0; h < NC; ++h) {
+                                const int uh = h ? u1 : u0;
+                                cpk x[8];
+                                load8_u8(pb + 16 * uh, x);
+                                const float f0 = (float)(b * GR_N + 8 * uh + 1);
+                                cpk s0 = cpk_make(0.f, 0.f), s1 = s0;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const cf e = nco_exact(w32, phase32, f0 + (float)i);
+                                    const cpk y = cpk_cmul(true_sample_pk(x[i]), e.x, e.y);
+                                    if (fold_on) A[8 * h + i] = cpk_add(A[8 * h + i], y);
+                                    const cpk c2 = cpk_make(cc[8 * h + i], cc[8 * h + i]);
+                                    if (i & 1) s1 = cpk_fma(y, c2, s1); else s0 = cpk_fma(y, c2, s0);
+                                }
+                                float re, im;
+                                cpk_split(cpk_add(s0, s1), re, im);
+                                const int k = b + 1 - ((h ? wr1 : wr0) ? 1 : 0);
+                                float2 acc = part2[k * NT + t];
+                                acc.x += re; acc.y += im;
+                                part2[k * NT + t] = acc;
+                            }
+                        }
+                        __syncthreads();
+                        if (t <= n_cyc) {                                     // B_k: the d & 7 samples in front of the boundary, pass k = t
+                            cf bsum = cf{0.f, 0.f};
+                            if (t >= 1) {
+                                cpk x[8];
+                                load8_u8(stage + (size_t)(t - 1) * (GR_N * 2) + 16 * dq, x);
+                                const float f0 = (float)((t - 1) * GR_N + 8 * dq + 1);
+#pragma unroll
+                                for (int i = 0; i < 7; ++i) {
+                                    const cf e = nco_exact(w32, phase32, f0 + (float)i);
+                                    float yr, yi;
+                                    cpk_split(cpk_cmul(true_sample_pk(x[i]), e.x, e.y), yr, yi);
+                                    const float c = S->qb[i].x;
+                                    bsum.x = fmaf(yr, c, bsum.x);
+                                    bsum.y = fmaf(yi, c, bsum.y);
+                                }
+                            }
+                            S->red[t].z = bsum.x;
+                            S->red[t].w = bsum.y;
+                        }
+                        {   // reduce the rows: warp w takes rows w, w + NT / 32, ...
+                            const int w = t >> 5, l = t & 31;
+                            for (int r = w; r <= n_cyc; r += NT / 32) {
+                                float2 v = part2[r * NT + l];
+#pragma unroll
+                                for (int m = 1; m < NT / 32; ++m) {
+                                    const float2 u = part2[r * NT + l + 32 * m];
+                                    v.x += u.x; v.y += u.y;
+                                }
+                                v.x = warp_sum(v.x); v.y = warp_sum(v.y);
+                                if (l == 0) { S->red[r].x = v.x; S->red[r].y = v.y; }
+                            }
+                        }
+                        __syncthreads();                                      // the rows are read: the buffer is free for the exchange
+#pragma unroll
+                        for (int i = 0; i < 8 * NC; ++i) cpk_split(A[i], G[i].x, G[i].y);
+                    } else {
+                        cf rsum;
+                        fold_blocks_vec<NC>(A, rsum, stage, (n_cyc - corr_avg) / 2, corr_avg, u0, u1, S->Rm);
+#pragma unroll
+                        for (int i = 0; i < 8 * NC; ++i) {
+                            float ar, ai;
+                            cpk_split(A[i], ar, ai);
+                            const cf r = cmul(i < 8 ? E0 : E1, S->sigma[i & 7]);
+                            G[i] = cmul(affine_sum<IN_FMT>(cf{ar, ai}, rsum), r);
+                        }
                     }
                     aex_write(ex, u0, G);
                     if (NC == 2) aex_write(ex, u1, G + 8 * (NC - 1));
@@ -673,10 +821,11 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                     corr_and_stats<kDense, kWide>(F, cs, 1.0f / ((float)corr_avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
                 }
             } else {
-                rt = nco_setup(w32, phase32, n_cyc, t, S);
+                if (!kExact) rt = nco_setup(w32, phase32, n_cyc, t, S);
                 __syncthreads();
                 cf F[16];
-                fold_blocks<IN_FMT, kStage>(F, src, (n_cyc - corr_avg) / 2, corr_avg, rt, t, S);
+                if (kExact) fold_blocks_exact<IN_FMT, kStage>(F, src, (n_cyc - corr_avg) / 2, corr_avg, w32, phase32, t);
+                else fold_blocks<IN_FMT, kStage>(F, src, (n_cyc - corr_avg) / 2, corr_avg, rt, t, S);
                 corr_and_stats<kDense>(F, cs, 1.0f / ((float)corr_avg * (float)GR_N), fftbuf, tw1, tw2, t, S);
             }
             if (t == 0) {                                    // same thread as the statistics above: no barrier in between
@@ -699,6 +848,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
             // ---- prompt integrate & dump (decodeData) ----
             const int d = S->delay;
             if constexpr (kVec) {
+              if (!kExact || d != d_spec) {                   // exact form: the fused pass above already holds the sums for d_spec
                 // Vector form: pass k sums the 2048 samples from 8 (d >> 3) + 2048 (k - 1) on, thread t its chunks u0, u1
                 // (a chunk whose index ran past 255 lies in the next block: "wrapped").  The code-period boundary d sits
                 // inside thread 0's first chunk: the d & 7 samples in front of it (B_k) are summed once more by thread k
@@ -708,12 +858,26 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                     dq = d >> 3;
                     u0 = (t + dq) & 255;
                     u1 = u0 ^ 128;
-                    E0 = chunk_rot(w32, phase32, u0);
-                    if (NC == 2) E1 = chunk_rot(w32, phase32, u1);
+                    if (!kExact) {
+                        E0 = chunk_rot(w32, phase32, u0);
+                        if (NC == 2) E1 = chunk_rot(w32, phase32, u1);
+                    }
                 }
                 const bool wr0 = t + dq >= 256, wr1 = t + dq + 128 >= 256;
-                float qr[8 * NC], qi[8 * NC];
-                {
+                float qr[8 * NC], qi[8 * NC];                           // fast form: rotation x code; exact form: qr = code only
+                if constexpr (kExact) {
+#pragma unroll
+                    for (int h = 0; h < NC; ++h) {
+                        const int uh = h ? u1 : u0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float c = S->code[(8 * uh + i - d) & (GR_N - 1)];
+                            qr[8 * h + i] = c;
+                            qi[8 * h + i] = 0.f;
+                            if (h == 0 && t == 0) S->qb[i] = cf{i < r8 ? c : 0.f, 0.f};
+                        }
+                    }
+                } else {
                     cf qall = cf{0.f, 0.f}, qw = cf{0.f, 0.f}, qbs = cf{0.f, 0.f};
                     const cf R1 = S->Rm[2];
 #pragma unroll
@@ -761,6 +925,22 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                         if (NC == 2) load8_u8(p1 + (size_t)(v1 ? b1 : 0) * (GR_N * 2), y);
                         // sum x q per chunk: two FFMA2 per sample, two independent chains per chunk (even / odd samples)
                         cpk a0 = cpk_make(0.f, 0.f), a1 = a0, b0e = a0, b1e = a0;
+                        if constexpr (kExact) {
+                            // q = e(n) c: the reference's factor of this very sample (block b0 / b1 of the epoch)
+                            const float f0 = (float)((v0 ? b0 : 0) * GR_N + 8 * u0 + 1);
+                            const float f1 = (float)((v1 ? b1 : 0) * GR_N + 8 * u1 + 1);
+#pragma unroll
+                            for (int i = 0; i < 8; i += 2) {
+                                const cf e0 = nco_exact(w32, phase32, f0 + (float)i), e1 = nco_exact(w32, phase32, f0 + (float)(i + 1));
+                                a0 = cpk_mac(a0, true_sample_pk(x[i]), e0.x * qr[i], e0.y * qr[i]);
+                                b0e = cpk_mac(b0e, true_sample_pk(x[i + 1]), e1.x * qr[i + 1], e1.y * qr[i + 1]);
+                                if (NC == 2) {
+                                    const cf g0 = nco_exact(w32, phase32, f1 + (float)i), g1 = nco_exact(w32, phase32, f1 + (float)(i + 1));
+                                    a1 = cpk_mac(a1, true_sample_pk(y[i]), g0.x * qr[8 * (NC - 1) + i], g0.y * qr[8 * (NC - 1) + i]);
+                                    b1e = cpk_mac(b1e, true_sample_pk(y[i + 1]), g1.x * qr[8 * (NC - 1) + i + 1], g1.y * qr[8 * (NC - 1) + i + 1]);
+                                }
+                            }
+                        } else {
 #pragma unroll
                         for (int i = 0; i < 8; i += 2) {
                             a0 = cpk_mac(a0, x[i], qr[i], qi[i]);
@@ -769,6 +949,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                                 a1 = cpk_mac(a1, y[i], qr[8 * (NC - 1) + i], qi[8 * (NC - 1) + i]);
                                 b1e = cpk_mac(b1e, y[i + 1], qr[8 * (NC - 1) + i + 1], qi[8 * (NC - 1) + i + 1]);
                             }
+                        }
                         }
                         a0 = cpk_add(a0, b0e);
                         a1 = cpk_add(a1, b1e);
@@ -785,11 +966,13 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                         if (t >= 1) {
                             cpk x[8];
                             load8_u8(stage + (size_t)(t - 1) * (GR_N * 2) + 16 * dq, x);
+                            const float f0 = (float)((t - 1) * GR_N + 8 * dq + 1);
 #pragma unroll
                             for (int i = 0; i < 7; ++i) {
                                 float xr, xi;
-                                cpk_split(x[i], xr, xi);
-                                const cf qm = S->qb[i];
+                                cpk_split(kExact ? true_sample_pk(x[i]) : x[i], xr, xi);
+                                cf qm = S->qb[i];
+                                if (kExact) { const cf e = nco_exact(w32, phase32, f0 + (float)i); qm = cf{e.x * qm.x, e.y * qm.x}; }
                                 bsum.x = fmaf(xr, qm.x, bsum.x); bsum.x = fmaf(-xi, qm.y, bsum.x);
                                 bsum.y = fmaf(xr, qm.y, bsum.y); bsum.y = fmaf(xi, qm.x, bsum.y);
                             }
@@ -797,7 +980,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                         S->red[t].z = bsum.x;
                         S->red[t].w = bsum.y;
                     }
-                    if (k0 == 0 && t >= 96 && t < 102) {
+                    if (!kExact && k0 == 0 && t >= 96 && t < 102) {
                         float qv = (S->qred[0][t - 96] + S->qred[1][t - 96]) + (S->qred[2][t - 96] + S->qred[3][t - 96]);
                         if (kWide) qv += (S->qred[4][t - 96] + S->qred[5][t - 96]) + (S->qred[6][t - 96] + S->qred[7][t - 96]);
                         S->qsum[t - 96] = qv;
@@ -817,11 +1000,16 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                     }
                     __syncthreads();
                 }
+              }
             } else {
                 const int jb = d >> 7, dlow = d & 127;
                 const bool inB = t < dlow;                       // row 0, before the code-period boundary
                 cf q[16];
-                {
+                float cj[kExact ? 16 : 1];                       // exact form: the code values of this thread's 16 rows
+                if constexpr (kExact) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) cj[kExact ? j : 0] = S->code[(t + 128 * ((j + jb) & 15) - d) & (GR_N - 1)];
+                } else {
                     cf qall = cf{0.f, 0.f}, qw = cf{0.f, 0.f};
                     const cf R1 = S->Rm[2];
     #pragma unroll
@@ -856,9 +1044,13 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                             const bool wrapped = (j + jb) >= 16;
                             const bool valid = vmode == 0 || (vmode == 1 ? wrapped : !wrapped);
                             const long long n = valid ? base + 128 * j : (long long)t;
-                            const cf v = load_raw<IN_FMT, kStage>(src, n);
+                            const cf v = kExact ? load_true<IN_FMT, kStage>(src, n) : load_raw<IN_FMT, kStage>(src, n);
                             x[j].x = valid ? v.x : 0.f;
                             x[j].y = valid ? v.y : 0.f;
+                            if constexpr (kExact) {                 // q = e(n) c: the reference's factor of this very sample
+                                const cf e = nco_exact(w32, phase32, (float)((int)n + 1));
+                                q[j] = cf{e.x * cj[kExact ? j : 0], e.y * cj[kExact ? j : 0]};
+                            }
                         }
                         cf p0 = cmul(x[0], q[0]);
                         cf acc = p0;
@@ -873,7 +1065,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                         part[(k - k0) * 128 + t] = make_float4(acc.x, acc.y, p0.x, p0.y);
                     }
                     __syncthreads();
-                    if (k0 == 0 && t >= 96 && t < 102)
+                    if (!kExact && k0 == 0 && t >= 96 && t < 102)
                         S->qsum[t - 96] = (S->qred[0][t - 96] + S->qred[1][t - 96]) + (S->qred[2][t - 96] + S->qred[3][t - 96]);
                     {   // reduce the staged rows: warp w takes rows w, w+4, ...
                         const int w = t >> 5, l = t & 31;
@@ -920,9 +1112,14 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                                                : (k == n_cyc ? cf{S->qsum[0] - S->qsum[4], S->qsum[1] - S->qsum[5]} : cf{S->qsum[0], S->qsum[1]});
                         cf X = affine_sum<IN_FMT>(cf{v.x, v.y}, Qk);
                         cf XB = (k == 0) ? cf{0.f, 0.f} : affine_sum<IN_FMT>(cf{v.z, v.w}, cf{S->qsum[2], S->qsum[3]});
+                        if constexpr (kExact) {                     // the sums are already those of the rotated true samples
+                            X = cf{v.x, v.y};
+                            XB = (k == 0) ? cf{0.f, 0.f} : cf{v.z, v.w};
+                        } else {
                         const cf R = S->Rm[k];
                         X = cmul(X, R);
                         XB = cmul(XB, R);
+                        }
                         xsw[k] = make_float4(X.x, X.y, XB.x, XB.y);
                     }
                 }
@@ -1307,14 +1504,19 @@ extern "C" int gr_track_bank_create(const gr_track_cfg* cfg, gr_track_bank** ban
     GR_CUDA(cudaMemset(b->d_state, 0, sizeof(GrChan) * (size_t)cfg->max_channels));
     GR_CUDA(cudaMalloc((void**)&b->d_slots, sizeof(int32_t) * (size_t)cfg->max_channels));
     GR_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)track_smem_bytes()));
-    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_CF32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)track_smem_bytes()));
-    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(track_smem_bytes() + track_stage_bytes(GR_MAX_NCYC))));
-    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(track_smem_bytes() + track_stage_bytes(GR_MAX_NCYC))));
-    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(track_smem_bytes() + track_stage_bytes(GR_MAX_NCYC))));
+    {
+        const char* fast = getenv("GPSB200_TRK_FAST_NCO");
+        b->exact_nco = !(fast && atoi(fast) != 0);
+    }
+    const int plain = (int)track_smem_bytes(), staged = (int)(track_smem_bytes() + track_stage_bytes(GR_MAX_NCYC));
+#define GR_TRK_ATTR(EX)                                                                                                             \
+    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, false, false, 128, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, plain));   \
+    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_CF32, false, false, 128, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, plain));   \
+    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true, false, 128, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, staged));   \
+    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true, true, 128, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, staged));    \
+    GR_CUDA(cudaFuncSetAttribute(track_kernel<GR_IN_U8IQ, true, false, 256, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, staged));
+    if (b->exact_nco) { GR_TRK_ATTR(true) } else { GR_TRK_ATTR(false) }
+#undef GR_TRK_ATTR
     gr_lib()->live_handles += 1;
     *bank = b;
     return GR_OK;
@@ -1413,6 +1615,7 @@ extern "C" int gr_track_num_active(const gr_track_bank* b) {
 }
 
 extern "C" int gr_track_last_launches(const gr_track_bank* b) { return b ? b->last_launches : 0; }
+extern "C" int gr_track_bank_form(const gr_track_bank* b) { return b && b->exact_nco ? GR_TRK_FORM_EXACT : GR_TRK_FORM_FAST; }
 
 extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int64_t rec_stride, int n_epochs,
                                     int64_t smp_time, gr_epoch_out* d_out, void* stream) {
@@ -1472,18 +1675,22 @@ extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int
         dense = dense_fits && !strcmp(form_env, "dense");
         wide = a.stage && !strcmp(form_env, "wide");
     }
+    // the exact form's fused pass keeps one partial prompt sum per thread and pass in the scratch buffer
+    if (b->exact_nco && (size_t)(b->cfg.n_cyc + 1) * 256 * 8 > (size_t)GR_TRACK_BUF_BYTES) wide = false;
     if (dense) {
         a.buf_bytes = (int)track_dense_buf_bytes(b->cfg.n_cyc);
         a.part_rows = track_dense_rows(b->cfg.n_cyc);
-        track_kernel<GR_IN_U8IQ, true, true><<<a.n_active, GR_FFT_THREADS, dense_smem, s>>>(a);
-    } else if (wide)
-        track_kernel<GR_IN_U8IQ, true, false, 256><<<a.n_active, 256, track_smem_bytes() + track_stage_bytes(b->cfg.n_cyc), s>>>(a);
-    else if (a.stage)
-        track_kernel<GR_IN_U8IQ, true><<<a.n_active, GR_FFT_THREADS, track_smem_bytes() + track_stage_bytes(b->cfg.n_cyc), s>>>(a);
-    else if (b->cfg.in_format == GR_IN_U8IQ)
-        track_kernel<GR_IN_U8IQ, false><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);
-    else
-        track_kernel<GR_IN_CF32, false><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);
+    }
+    const size_t staged_smem = track_smem_bytes() + track_stage_bytes(b->cfg.n_cyc);
+#define GR_TRK_LAUNCH(EX)                                                                                                   \
+    if (dense) track_kernel<GR_IN_U8IQ, true, true, 128, EX><<<a.n_active, GR_FFT_THREADS, dense_smem, s>>>(a);                 \
+    else if (wide) track_kernel<GR_IN_U8IQ, true, false, 256, EX><<<a.n_active, 256, staged_smem, s>>>(a);                       \
+    else if (a.stage) track_kernel<GR_IN_U8IQ, true, false, 128, EX><<<a.n_active, GR_FFT_THREADS, staged_smem, s>>>(a);          \
+    else if (b->cfg.in_format == GR_IN_U8IQ)                                                                                 \
+        track_kernel<GR_IN_U8IQ, false, false, 128, EX><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);               \
+    else track_kernel<GR_IN_CF32, false, false, 128, EX><<<a.n_active, GR_FFT_THREADS, track_smem_bytes(), s>>>(a);
+    if (b->exact_nco) { GR_TRK_LAUNCH(true) } else { GR_TRK_LAUNCH(false) }
+#undef GR_TRK_LAUNCH
     GR_CUDA(cudaGetLastError());
     GR_CUDA(cudaEventRecord(b->ev_last, s));
     b->in_flight = true;

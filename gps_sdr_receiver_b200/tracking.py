@@ -70,6 +70,12 @@ class TrackBank:
     def launches(self) -> int:
         return _capi.lib().gr_track_last_launches(self._h)
 
+    @property
+    def form(self) -> str:
+        """'exact' (default: the reference's float32 phase argument for every sample, gpslib.py:1343-1346) or 'fast'
+        (factorised NCO, GPSB200_TRK_FAST_NCO=1 when the bank was created); see include/gps_b200.h."""
+        return "exact" if _capi.lib().gr_track_bank_form(self._h) else "fast"
+
     def process(self, samples, smp_time: int, n_epochs: int = 1, nrec: int = 1, rec_stride: int | None = None,
                 out: np.ndarray | None = None) -> np.ndarray:
         """Host buffers in, host records out.  Returns EPOCH_OUT[n_epochs, n_active]."""

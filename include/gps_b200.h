@@ -197,6 +197,14 @@ int gr_track_process_host(gr_track_bank* bank, const void* h_samples, int64_t re
                           int n_epochs, int64_t smp_time, gr_epoch_out* h_out);
 int gr_track_num_active(const gr_track_bank* bank);
 int gr_track_last_launches(const gr_track_bank* bank);
+/* NCO form of the bank's kernel.  EXACT (default): every sample is rotated by the reference's own float32 phase argument
+ * exp(-i fl32(PHASE + fl32(w * SEC_TIME[n]))) (gpslib.py:1343-1346).  FAST (GPSB200_TRK_FAST_NCO=1 when the bank is
+ * created): the rotation is factorised (2 sin/cos per thread and epoch) and mathematically exact, i.e. it does not
+ * carry the reference's per-sample float32 argument noise (6e-5 rad at 5 kHz x 32 ms): same decisions, FREQ a few float32
+ * ulp apart, carrier phase / complex prompts up to 1e-4 / 5e-4 rad apart. */
+#define GR_TRK_FORM_FAST 0
+#define GR_TRK_FORM_EXACT 1
+int gr_track_bank_form(const gr_track_bank* bank);
 
 /* ---- synthetic recordings (measurement / test infrastructure) ------------ */
 typedef struct gr_synth_sat {
