@@ -138,6 +138,11 @@ FORM_TEXT = {
     "fast": "fast: one forward spectrum per 1-kHz class of bins, blocks 1..9 of a coherent interval rotated by one "
             "exp(-i w 2048 b / fs) per block (block 0 with the reference's float32 argument per sample)",
 }
+TRACK_FORM_TEXT = {
+    "exact": "exact (default): every sample rotated by the reference's own float32 phase argument fl32(PHASE + fl32(w * SEC_TIME[n])) "
+             "(gpslib.py:1343-1346), once, in a fused fold + prompt pass",
+    "fast": "fast: factorised NCO (2 sin/cos per thread and epoch), two sample passes",
+}
 FINE_BINS = [-10000.0 + 50.0 * b for b in range(401)]
 FINE_TCOH, FINE_K = 10, 20
 _FINE_RAW = None
@@ -585,6 +590,7 @@ def run_b200(args):
             return bank
 
         wb = new_bank()
+        track_form = wb.form
         for _ in range(3):
             wb.process_dev(rec, ngps, min(n_ep, 500), out=out_dev[:min(n_ep, 500)])
         wb.close()
@@ -638,7 +644,7 @@ def run_b200(args):
             "config": {"workload": f"steady-state tracking: {TRACK_NCH} channels, 8-ms epochs (N_CYC=8), {args.track_seconds:.0f} s synthetic "
                                    "recording per GPU, loop filters on device (BASELINE configs[2])",
                        "epochs": n_ep, "launches_per_recording": 1, "multi_gpu": "replicas only: one recording per rank"},
-            "seconds": t_track, "reps": args.track_reps,
+            "seconds": t_track, "reps": args.track_reps, "form": TRACK_FORM_TEXT[track_form],
             "e2e": {"value": world * args.track_seconds / t_te2e, "unit": "x-realtime", "h2d_bytes": raw_bytes, "d2h_bytes": rec_bytes,
                     "gpu_launches": tl, "api": "TrackBank.process -> gr_track_process_host (3-stream chunk pipeline), pinned host buffers"},
             "roofline": {"bound": "hbm", "kernel": "track_kernel", "achieved": (raw_bytes + rec_bytes) / t_track / 1e9, "peak": hbm_peak,
@@ -678,24 +684,34 @@ def run_b200(args):
             wb = new_batch_bank()
             wb.process_dev(brec, ngps, min(nb_ep, 200), rec_stride=span, out=bout[:min(nb_ep, 200)])
             wb.close()
-            bank = new_batch_bank()
-            barrier()
-            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t_a = time.perf_counter()
-            b0.record()
-            bank.process_dev(brec, ngps, nb_ep, rec_stride=span, out=bout)
-            b1.record()
-            barrier()
-            windows.append((t_a, time.perf_counter()))
-            t_batch = max_over_ranks(b0.elapsed_time(b1)) * 1e-3
-            last = TrackBank.records_from_tensor(bout[nb_ep - 1:nb_ep])[0]
-            assert int((last["locked"] == 1).sum()) == RB * TRACK_NCH, "a batched channel lost lock"
-            bank.close()
+            def time_batch():
+                bank = new_batch_bank()
+                form = bank.form
+                barrier()
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t_a = time.perf_counter()
+                b0.record()
+                bank.process_dev(brec, ngps, nb_ep, rec_stride=span, out=bout)
+                b1.record()
+                barrier()
+                windows.append((t_a, time.perf_counter()))
+                tb = max_over_ranks(b0.elapsed_time(b1)) * 1e-3
+                last = TrackBank.records_from_tensor(bout[nb_ep - 1:nb_ep])[0]
+                assert int((last["locked"] == 1).sum()) == RB * TRACK_NCH, "a batched channel lost lock"
+                bank.close()
+                return tb, form
+
+            t_batch, batch_form = time_batch()
+            os.environ["GPSB200_TRK_FAST_NCO"] = "1"            # the factorised NCO (not the parity-verified default), for comparison
+            t_batch_fast, _ = time_batch()
+            del os.environ["GPSB200_TRK_FAST_NCO"]
             b_raw = 2 * RB * span
             b_out = nb_ep * RB * TRACK_NCH * EPOCH_OUT.itemsize
             line["tracking_batch"] = {
                 "metric": "tracking x-realtime, aggregate over independent recordings", "value": world * RB * secs / t_batch,
-                "unit": "x-realtime", "seconds": t_batch,
+                "unit": "x-realtime", "seconds": t_batch, "form": TRACK_FORM_TEXT[batch_form],
+                "fast_form": {"value": world * RB * secs / t_batch_fast, "unit": "x-realtime", "seconds": t_batch_fast,
+                              "form": "GPSB200_TRK_FAST_NCO=1 (forced): " + TRACK_FORM_TEXT["fast"]},
                 "config": {"workload": f"{RB} recordings x {TRACK_NCH} channels per GPU, {secs:.0f} s each, 8-ms epochs, one launch "
                                        f"({RB * TRACK_NCH} channel CTAs, all resident: 3 per SM in the kernel's dense form; per-GPU share of BASELINE configs[4])"},
                 "roofline": {"bound": "hbm", "kernel": "track_kernel", "achieved": (b_raw + b_out) / t_batch / 1e9, "peak": hbm_peak,
@@ -708,7 +724,7 @@ def run_b200(args):
                              "note": "algorithmic bytes = each recording's raw I/Q once + one record per channel-epoch; the kernel is "
                                      "FP32/latency-bound (about 260 flop per byte, DESIGN.md 4.3), so the HBM fraction stays small by construction"},
             }
-            line["gpu_launches"] += 1
+            line["gpu_launches"] += 2
             del bout
 
             # ---- configs[4] per GPU: acquisition -> hand-over -> tracking -> NCCL gather of the per-stream results ----

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgpsb200.so")
+LIB_PATH = os.environ.get("GPSB200_LIB") or os.path.join(HERE, "libgpsb200.so")      # GPSB200_LIB: A/B runs against another build
 
 GR_OK = 0
 GR_IN_U8IQ, GR_IN_CF32 = 0, 1
