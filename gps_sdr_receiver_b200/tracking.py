@@ -46,7 +46,10 @@ class TrackBank:
 
     def close(self):
         if getattr(self, "_h", None):
-            _capi.lib().gr_track_bank_destroy(self._h)
+            try:
+                _capi.lib().gr_track_bank_destroy(self._h)
+            except TypeError:          # interpreter teardown: the module globals are already gone
+                pass
             self._h = None
 
     __del__ = close
