@@ -36,14 +36,13 @@ struct GrTables {
 // 232-235; gpslib.py:1053-1054, 1343-1346).  At |w t| ~ 1e3 .. 1e4 rad the float32 rounding of that argument (6e-5 .. 1e-3
 // rad) is the largest term in the distance between the reference and the mathematically exact rotation, so the forms
 // of the kernels that have to stay within 1e-4 of the reference evaluate the same argument per sample.
-// fl32(k / fs) for an integer-valued float k < 2^23 in three instructions: quotient estimate, exact remainder, one
-// correction.  Equal to the correctly rounded IEEE division for every k = 1 .. 2^23 (checked exhaustively on the host);
-// the generic division is ~10 instructions with a slow-path branch.
+// fl32(k / fs) for an integer-valued float k <= 2^23 in two instructions: 1 / fs as a two-term float32 sum y_hi + y_lo
+// (accurate to 2^-49), t = fma(k, y_hi, fl32(k * y_lo)).  Equal to the correctly rounded IEEE division for every
+// k = 1 .. 2^23 (checked exhaustively on the host, tests/test_capi_host.py); the generic division is ~10 instructions
+// with a slow-path branch, and the reference-exact forms of the kernels run one per sample.
 __device__ __forceinline__ float tsec_of(float k) {
-    const float y = 1.0f / GR_FS;
-    const float q0 = __fmul_rn(k, y);
-    const float r = __fmaf_rn(-q0, GR_FS, k);
-    return __fmaf_rn(r, y, q0);
+    return __fmaf_rn(k, __uint_as_float(889393775u) /* fl32(1 / fs) = 4.882812731921149e-07 */,
+                     __fmul_rn(k, __uint_as_float(2832262496u) /* fl32(1 / fs - y_hi) = -2.31921144615288e-14 */));
 }
 // exp(-i arg), |arg| < 2^22 turns: 2-constant Cody-Waite reduction (6.28125 = 201/32: k * C1 is exact) + MUFU sin / cos,
 // |err| < 5e-7; the rounding to a whole number of turns by the 1.5 * 2^23 trick (two full-rate additions, no FRND)

@@ -34,6 +34,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <type_traits>
 #include <vector>
 
 #include "gr_fft2048.cuh"
@@ -367,9 +368,11 @@ __device__ __forceinline__ void fold_blocks_vec(cpk* A, cf& rsum, const unsigned
 // from the reference on every sample (oracle/parity_floor.py: FREQ bit-equal on half the epochs only, complex prompts 4e-4
 // apart).  This form reproduces the argument itself (sin / cos of it to 5e-7) and pays N_CYC x 2048 x 2 sin / cos per epoch
 // and channel instead of 2 per thread.
-// reader's conversion, gpsrecv.py:168-173: complex64(raw) / 127.5 - (1 + 1j): two float32 roundings per component
+// reader's conversion, gpsrecv.py:168-173: complex64(raw) / 127.5 - (1 + 1j).  One FFMA2 here (b * fl32(1 / 127.5) - 1 with
+// one rounding; the reference rounds the product first: the two differ by at most one ulp of the sample, 6e-8, on a
+// few of the 256 byte values)
 __device__ __forceinline__ cpk true_sample_pk(cpk b) {
-    return cpk_add(cpk_mul(b, cpk_make(1.0f / 127.5f, 1.0f / 127.5f)), cpk_make(-1.f, -1.f));
+    return cpk_fma(b, cpk_make(1.0f / 127.5f, 1.0f / 127.5f), cpk_make(-1.f, -1.f));
 }
 template <int IN_FMT, bool kStage>
 __device__ __forceinline__ cf load_true(const void* base, long long n) {
@@ -738,8 +741,8 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                         for (int k = 0; k <= n_cyc; ++k) part2[k * NT + t] = make_float2(0.f, 0.f);
 #pragma unroll
                         for (int i = 0; i < 8 * NC; ++i) A[i] = cpk_make(0.f, 0.f);
-                        for (int b = 0; b < n_cyc; ++b) {
-                            const bool fold_on = b >= first && b < first + corr_avg;
+                        auto block = [&](int b, auto fold_tag) {           // one 1-ms block; fold_tag: it belongs to the coherent fold
+                            constexpr bool kFold = decltype(fold_tag)::value;
                             const unsigned char* pb = stage + (size_t)b * (GR_N * 2);
 #pragma unroll
                             for (int h = 0; h < NC; ++h) {
@@ -752,7 +755,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                                 for (int i = 0; i < 8; ++i) {
                                     const cf e = nco_exact(w32, phase32, f0 + (float)i);
                                     const cpk y = cpk_cmul(true_sample_pk(x[i]), e.x, e.y);
-                                    if (fold_on) A[8 * h + i] = cpk_add(A[8 * h + i], y);
+                                    if (kFold) A[8 * h + i] = cpk_add(A[8 * h + i], y);
                                     const cpk c2 = cpk_make(cc[8 * h + i], cc[8 * h + i]);
                                     if (i & 1) s1 = cpk_fma(y, c2, s1); else s0 = cpk_fma(y, c2, s0);
                                 }
@@ -763,7 +766,10 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                                 acc.x += re; acc.y += im;
                                 part2[k * NT + t] = acc;
                             }
-                        }
+                        };
+                        for (int b = 0; b < first; ++b) block(b, std::false_type{});
+                        for (int b = first; b < first + corr_avg; ++b) block(b, std::true_type{});
+                        for (int b = first + corr_avg; b < n_cyc; ++b) block(b, std::false_type{});
                         __syncthreads();
                         if (t <= n_cyc) {                                     // B_k: the d & 7 samples in front of the boundary, pass k = t
                             cf bsum = cf{0.f, 0.f};

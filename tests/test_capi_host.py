@@ -84,3 +84,24 @@ def test_fft2048_index_mapping_host_emulation(tmp_path):
     y = np.frombuffer(subprocess.run([exe], input=x.tobytes(), capture_output=True, check=True).stdout, dtype=np.complex64)
     r = np.fft.fft(x.astype(np.complex128))
     assert np.abs(y - r).max() < 1e-6 * np.abs(r).max()
+
+
+def test_two_instruction_time_base_equals_ieee_division_for_every_sample_index():
+    """csrc/gr_common.cuh `tsec_of`: the kernels' reference-exact NCO forms need t[n] = fl32((n + 1) / fs) (gpsrecv.py:32-33,
+    gpslib.py:1053-1054) per sample and form it as fma(k, y_hi, fl32(k * y_lo)) with 1 / fs = y_hi + y_lo.  Emulated here with
+    exact products (k * y_hi has 48 significant bits, the sum fits a 64-bit mantissa, one rounding to float32) for EVERY
+    k = 1 .. 2^23 against numpy's float32 division."""
+    fs = np.float32(2048000.0)
+    y_hi = np.array([889393775], dtype=np.uint32).view(np.float32)[0]
+    y_lo = np.array([2832262496], dtype=np.uint32).view(np.float32)[0]
+    assert y_hi == np.float32(1.0) / fs and y_lo == np.float32(1.0 / 2048000.0 - np.float64(y_hi))
+    if np.finfo(np.longdouble).nmant < 63:
+        pytest.skip("needs an 80-bit long double to emulate the fused multiply-add")
+    bad = 0
+    for lo in range(1, (1 << 23) + 1, 1 << 21):
+        k = np.arange(lo, min(lo + (1 << 21), (1 << 23) + 1), dtype=np.float64)
+        kf = k.astype(np.float32)
+        c = kf * y_lo                                                   # float32 product, rounded
+        t = (k.astype(np.longdouble) * np.longdouble(y_hi) + c.astype(np.longdouble)).astype(np.float32)
+        bad += int((t != kf / fs).sum())
+    assert bad == 0
