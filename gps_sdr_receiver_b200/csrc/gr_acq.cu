@@ -877,7 +877,8 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         return GR_ERR_ARG;
     }
     const size_t spec_per_rec = (size_t)p->nbase * p->nnoncoh * 2 * GR_N * sizeof(float2);
-    int sub = (int)(GR_ACQ_SPEC_CAP / spec_per_rec);
+    static const size_t spec_cap = getenv("GPSB200_ACQ_SPEC_MB") ? (size_t)atoi(getenv("GPSB200_ACQ_SPEC_MB")) << 20 : GR_ACQ_SPEC_CAP;
+    int sub = (int)(spec_cap / spec_per_rec);
     if (sub < 1) sub = 1;
     if (sub > nrec) sub = nrec;
     int rc = grow((void**)&p->d_spec, &p->spec_bytes, (size_t)sub * spec_per_rec);

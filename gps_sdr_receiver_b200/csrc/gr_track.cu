@@ -61,12 +61,20 @@ struct GrChanHot {
     double max_corr, corr_q, corr_l;
     float phase, amplitude;
 };
-struct GrChan {
-    GrChanHot h;                 // scalars: cached in shared memory while the kernel runs
+struct GrChanS {                 // the part of a channel's state that lives in shared memory while the kernel runs
+    GrChanHot h;                 // scalars
     float df[GR_DF_CAP];         // DF FIFO (ring)
     float df_save[GR_DF_CAP];
-    int8_t cl[GR_CL_CAP];        // CORRLST FIFO (ring) of +1/-1
 };
+struct GrChan {                  // global memory: GrChanS (same layout, copied in / out once per launch) + the CORRLST ring
+    GrChanHot h;
+    float df[GR_DF_CAP];
+    float df_save[GR_DF_CAP];
+    int8_t cl[GR_CL_CAP];        // CORRLST FIFO (ring) of +1/-1: one entry in, at most two out per epoch (exact integer running
+                                 // sums in `h`), touched by thread 0 only -- it stays in global memory, the two outgoing entries
+                                 // are fetched into registers at the start of the epoch
+};
+static_assert(offsetof(GrChan, cl) == sizeof(GrChanS), "GrChanS is the prefix of GrChan");
 
 struct gr_track_bank {
     gr_track_cfg cfg;
@@ -115,12 +123,10 @@ struct TrackArgs {
 struct TrackSmem {
     gr_epoch_out out[2];                 // the epoch's record is assembled here (448 B each, 16-byte aligned) and leaves by TMA
     unsigned long long rawbar;           // mbarrier of the raw-sample stage (first member: 8-byte aligned)
-    GrChan CH;                           // this channel's whole state (scalars + DF / CORRLST rings) for the life of the kernel
-    float code[GR_N];                    // resampled C/A code of this PRN
+    GrChanS CH;                          // this channel's scalars + DF rings for the life of the kernel
     cf rho[16];                          // exp(-i w 128 j / fs)
     cf Rm[GR_MAX_NCYC + 2];              // Rm[k] = R_{k-1} = exp(-i w (k-1) ms), k = 0..n_cyc
     float4 red[GR_MAX_NCYC + 2];         // reduced prompt rows: (S_k, B_k)
-    float4 xs[GR_MAX_NCYC + 2];          // (X_k, XB_k): affine-corrected, block-rotated
     float qred[8][6];                    // per-warp sums of q: all rows, masked row 0, wrapped rows
     cf sigma[8];                         // vector form: exp(-i w i / fs), i = 0..7
     cf qb[8];                            // vector form: the replica values of the samples between the window start 8 (d >> 3) and d
@@ -475,15 +481,15 @@ __device__ __forceinline__ void st_erase_prev(GrChanHot* c) {      // gpslib.py:
     c->carry_re = 0.0;
     c->carry_im = 0.0;
 }
-__device__ __forceinline__ void st_unlock(GrChanHot* c, GrChan* g) {          // gpslib.py:1102-1107
+__device__ __forceinline__ void st_unlock(GrChanHot* c, int8_t* cl) {          // gpslib.py:1102-1107
     c->locked = 0;
-    c->cl_len = 1; c->cl_head = 0; g->cl[0] = 0; c->cl_sum = 0; c->cl_sum_last = 0;
+    c->cl_len = 1; c->cl_head = 0; cl[0] = 0; c->cl_sum = 0; c->cl_sum_last = 0;
     c->ms_time = 0;
     c->phase = 0.f;
     st_erase_prev(c);
 }
-__device__ __forceinline__ void st_init_sweep(GrChanHot* c, GrChan* g, const gr_track_cfg& cfg) {   // gpslib.py:1110-1116
-    st_unlock(c, g);
+__device__ __forceinline__ void st_init_sweep(GrChanHot* c, GrChanS* g, int8_t* cl, const gr_track_cfg& cfg) {   // gpslib.py:1110-1116
+    st_unlock(c, cl);
     c->freq_save = c->freq;
     c->freq_save_weak = c->freq_weak;
     c->df_save_len = c->df_len;
@@ -502,22 +508,32 @@ __device__ __forceinline__ void st_corr_ratios(GrChanHot* c, int no_sec) {      
     const int nl = c->cl_len < no_sec ? c->cl_len : no_sec;
     c->corr_l = (double)c->cl_sum_last / (double)nl;
 }
+// The two entries that may leave the sums when the next one is appended: fetched at the start of the epoch (their indices
+// are known then), consumed by st_corr_quality several microseconds later.
+struct ClOut { int all, win; };
+__device__ __forceinline__ ClOut st_corr_prefetch(const GrChanHot* c, const int8_t* cl, int no_sec) {
+    const int cap = 60 * no_sec;
+    const int len = c->cl_len, head = c->cl_head;
+    int iw = head + len - no_sec;
+    iw -= iw >= GR_CL_CAP ? GR_CL_CAP : 0;
+    ClOut o;
+    o.all = (len + 1 > cap) ? (int)cl[head] : 0;
+    o.win = (len + 1 > no_sec) ? (int)cl[iw] : 0;
+    return o;
+}
 template <bool kRatios = true>
-__device__ __forceinline__ void st_corr_quality(GrChanHot* c, GrChan* g, double code_phase, int no_sec) {
+__device__ __forceinline__ void st_corr_quality(GrChanHot* c, int8_t* cl, ClOut out, double code_phase, int no_sec) {
     const int cap = 60 * no_sec;
     const int v = code_phase < 0.0 ? -1 : 1;
     const int len = c->cl_len, head = c->cl_head;
     const bool full = len + 1 > cap;                       // append, then pop the oldest
-    const int out_all = full ? (int)g->cl[head] : 0;
     // head, len <= GR_CL_CAP: the ring indices are below 2 GR_CL_CAP, one conditional subtraction instead of a modulo
-    int iw = head + len - no_sec, is = head + len, ih = head + 1;
-    iw -= iw >= GR_CL_CAP ? GR_CL_CAP : 0;
+    int is = head + len, ih = head + 1;
     is -= is >= GR_CL_CAP ? GR_CL_CAP : 0;
     ih -= ih >= GR_CL_CAP ? GR_CL_CAP : 0;
-    const int out_win = (len + 1 > no_sec) ? (int)g->cl[iw] : 0;
-    g->cl[is] = (int8_t)v;
-    c->cl_sum += v - out_all;
-    c->cl_sum_last += v - out_win;
+    cl[is] = (int8_t)v;
+    c->cl_sum += v - out.all;
+    c->cl_sum_last += v - out.win;
     if (full) c->cl_head = ih;
     else c->cl_len = len + 1;
     if (kRatios) st_corr_ratios(c, no_sec);
@@ -567,7 +583,8 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
     const int t = threadIdx.x;
     const int slot = a.slots[blockIdx.x];
     GrChan* Gg = a.state + slot;        // global copy: read once, written back at the end
-    GrChan* G = &S->CH;                 // rings are touched every epoch: keep them out of L2 latency
+    GrChanS* G = &S->CH;                // scalars and DF rings are touched every epoch: keep them out of L2 latency
+    int8_t* CL = Gg->cl;                // the CORRLST ring stays in global memory (see GrChan)
     const int n_cyc = a.cfg.n_cyc;
     const int ngps = n_cyc * GR_N;
     const int no_sec = 1024 / n_cyc;
@@ -576,7 +593,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
     const int prn = Gg->h.prn;
     const float2* cs = a.tab.conjspec + (size_t)prn * GR_N;
 
-    cf tw1[16], tw2[16];
+    cf tw1[16], tw2[16];                // FFT twiddles, in registers for the life of the kernel
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const float2 u = a.tab.tw1[(t & 127) * 16 + k];
@@ -584,8 +601,8 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
         tw1[k] = cf{u.x, u.y};
         tw2[k] = cf{v.x, v.y};
     }
-    for (int i = t; i < GR_N; i += NT) S->code[i] = a.tab.code[(size_t)prn * GR_N + i];
-    for (int i = t; i < (int)(sizeof(GrChan) / 4); i += NT)
+    const float* code_g = a.tab.code + (size_t)prn * GR_N;       // resampled C/A code of this PRN (8 KB, L1 / L2 resident)
+    for (int i = t; i < (int)(sizeof(GrChanS) / 4); i += NT)
         reinterpret_cast<uint32_t*>(G)[i] = reinterpret_cast<const uint32_t*>(Gg)[i];
     if (t == 0) {
         if (kStage) {
@@ -611,13 +628,14 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
         const bool report = (stream_no & (long long)(no_sec - 1)) == 0;
 
         // ---- epoch prologue (gpslib.py:1142-1151) ----
+        ClOut cl_out{0, 0};
         if (t == 0) {
             int erased = 0;
             if (stream_no - 1 != C->prev_stream_no) { st_erase_prev(C); erased = 1; }
             C->prev_stream_no = stream_no;
             const int req = C->sweep_req && !C->sweep;
             C->sweep_req = 0;
-            if (req) { st_init_sweep(C, G, a.cfg); erased = 1; }
+            if (req) { st_init_sweep(C, G, CL, a.cfg); erased = 1; }
             O->erased = erased;
             S->branch_sweep = C->sweep;
             S->carry0_cnt = C->carry_cnt; S->carry0_re = C->carry_re; S->carry0_im = C->carry_im;
@@ -636,6 +654,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
             O->rep_sweep = 0;
             O->report = report ? 1 : 0;
             O->prn = prn;
+            cl_out = st_corr_prefetch(C, CL, no_sec);       // two global loads in flight until the correlation decision
         }
         __syncthreads();
         if (kStage) trk_mbar_wait(&S->rawbar, e & 1);
@@ -680,7 +699,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                 C->freq = freq;
                 C->freq_weak = 1;
                 C->max_corr = z;
-                st_corr_quality(C, G, code_phase, no_sec);
+                st_corr_quality(C, CL, cl_out, code_phase, no_sec);
                 if (delay >= 0) C->delay = delay;
                 else if (!running) {                          // restoreFreq, gpslib.py:1118-1120
                     C->freq = C->freq_save;
@@ -733,7 +752,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                             const int uh = h ? u1 : u0;
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                cc[8 * h + i] = S->code[(8 * uh + i - d_spec) & (GR_N - 1)];
+                                cc[8 * h + i] = __ldg(code_g + ((8 * uh + i - d_spec) & (GR_N - 1)));
                                 if (h == 0 && t == 0) S->qb[i] = cf{i < r8s ? cc[i] : 0.f, 0.f};
                             }
                         }
@@ -841,7 +860,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                     delay = S->sh_i[4];
                     code_phase = fit_code_phase(delay, (double)S->c3[0], (double)S->c3[1], (double)S->c3[2]);
                 }
-                st_corr_quality<false>(C, G, code_phase, no_sec);      // integer sums now, the two FP64 means by thread 96 later
+                st_corr_quality<false>(C, CL, cl_out, code_phase, no_sec);      // integer sums now, the two FP64 means by thread 96 later
                 if (delay >= 0) C->delay = delay;
                 S->corr_delay = delay;
                 S->code_phase = code_phase;
@@ -877,7 +896,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                         const int uh = h ? u1 : u0;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float c = S->code[(8 * uh + i - d) & (GR_N - 1)];
+                            const float c = __ldg(code_g + ((8 * uh + i - d) & (GR_N - 1)));
                             qr[8 * h + i] = c;
                             qi[8 * h + i] = 0.f;
                             if (h == 0 && t == 0) S->qb[i] = cf{i < r8 ? c : 0.f, 0.f};
@@ -894,7 +913,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                         if (wr) Eh = cmul(Eh, R1);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float c = S->code[(8 * uh + i - d) & (GR_N - 1)];
+                            const float c = __ldg(code_g + ((8 * uh + i - d) & (GR_N - 1)));
                             const cf r = cmul(Eh, S->sigma[i]);
                             const cf q = cf{r.x * c, r.y * c};
                             qr[8 * h + i] = q.x;
@@ -1014,7 +1033,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                 float cj[kExact ? 16 : 1];                       // exact form: the code values of this thread's 16 rows
                 if constexpr (kExact) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) cj[kExact ? j : 0] = S->code[(t + 128 * ((j + jb) & 15) - d) & (GR_N - 1)];
+                    for (int j = 0; j < 16; ++j) cj[kExact ? j : 0] = __ldg(code_g + ((t + 128 * ((j + jb) & 15) - d) & (GR_N - 1)));
                 } else {
                     cf qall = cf{0.f, 0.f}, qw = cf{0.f, 0.f};
                     const cf R1 = S->Rm[2];
@@ -1023,7 +1042,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                         const int row = (j + jb) & 15;
                         const bool wrapped = (j + jb) >= 16;
                         const int i = t + 128 * row;
-                        const float c = S->code[(i - d) & (GR_N - 1)];
+                        const float c = __ldg(code_g + ((i - d) & (GR_N - 1)));
                         cf r = cmul(rt, S->rho[row]);
                         if (wrapped) r = cmul(r, R1);
                         q[j] = cf{r.x * c, r.y * c};
@@ -1429,7 +1448,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
         __syncthreads();
         if (S->do_sweep) {                                   // quality-triggered re-sweep (gpslib.py:1134-1138, 1198-1203): rare; uniform
             if (t == 0) {
-                st_init_sweep(C, G, a.cfg);
+                st_init_sweep(C, G, CL, a.cfg);
                 O->erased |= 2;
                 O->sweep = C->sweep;
                 O->locked = C->locked;
@@ -1457,7 +1476,7 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
     }
     if (t == 0 && a.out_tma) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncthreads();
-    for (int i = t; i < (int)(sizeof(GrChan) / 4); i += NT)
+    for (int i = t; i < (int)(sizeof(GrChanS) / 4); i += NT)
         reinterpret_cast<uint32_t*>(Gg)[i] = reinterpret_cast<const uint32_t*>(G)[i];
 }
 
@@ -1466,7 +1485,9 @@ static size_t track_smem_bytes(size_t buf_bytes = GR_TRACK_BUF_BYTES) { return b
 // dense form: one-buffer FFT, prompt rows staged min(n_cyc + 1, GR_PART_ROWS) at a time
 static int track_dense_rows(int n_cyc) { return n_cyc + 1 < GR_PART_ROWS ? n_cyc + 1 : GR_PART_ROWS; }
 static size_t track_dense_buf_bytes(int n_cyc) {
-    const size_t rows = (size_t)track_dense_rows(n_cyc) * 128 * 16;
+    // the dense form is the vector form (staged uint8 I/Q): its prompt rows are float2 per thread (8 bytes), and the FFT runs
+    // in its one-buffer mode
+    const size_t rows = (size_t)track_dense_rows(n_cyc) * 128 * 8;
     return rows > GR_ONEBUF_BYTES ? rows : (size_t)GR_ONEBUF_BYTES;
 }
 static size_t track_stage_bytes(int n_cyc) { return (size_t)n_cyc * GR_N * 2; }
@@ -1674,7 +1695,7 @@ extern "C" int gr_track_process_dev(gr_track_bank* b, const void* d_samples, int
     const char* form_env = getenv("GPSB200_TRACK_FORM");
     const char* dense_env = getenv("GPSB200_TRACK_DENSE");
     const size_t dense_smem = track_smem_bytes(track_dense_buf_bytes(b->cfg.n_cyc)) + track_stage_bytes(b->cfg.n_cyc);
-    const bool dense_fits = a.stage && 3 * (dense_smem + 1024) <= 227 * 1024;
+    const bool dense_fits = a.stage && 3 * (dense_smem + 1024) <= 228 * 1024;
     bool dense = dense_fits && (dense_env ? atoi(dense_env) != 0 : a.n_active > 2 * gr_lib()->num_sms);
     bool wide = a.stage && !dense && !dense_env && a.n_active <= gr_lib()->num_sms;
     if (form_env) {
