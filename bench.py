@@ -366,6 +366,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     windows.append((t_a, time.perf_counter()))
     ms_kernel = k0.elapsed_time(k1) / args.steps
+    inv_kernel_name = plan.inverse_kernel()        # the launcher picks the form of the inverse kernel per call (include/gps_b200.h)
     achieved_tf = R * FLOP_PER_REC / (ms_kernel * 1e-3) / 1e12
 
     # end to end through the public host API: pinned host I/Q in, host tuples out, every step
@@ -401,7 +402,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": R * REC_SAMPLES * 2,
                 "d2h_bytes_per_step": R * NPRN * ACQ_BEST.itemsize, "api": "AcqPlan.search -> gr_acq_search_host (C ABI), pinned host buffers"},
         "gpu_launches": launches,
-        "roofline": {"bound": "fp32", "kernel": "acq_inv_kernel (+ acq_fwd_kernel, 0.5 % of the launch pair)", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+        "roofline": {"bound": "fp32", "kernel": inv_kernel_name + " (+ acq_fwd_kernel, 0.5 % of the launch pair)", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp32_peak,
                      # dram__bytes_read + dram__bytes_write of the kernel pair, ncu --set full capture of 128 recordings
                      # (profiles/acq_r01_v8_ncu_summary.md: 5.3 + 25.5 MB forward, 94.6 + 7.0 MB inverse), scaled to R

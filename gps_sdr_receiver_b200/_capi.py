@@ -78,6 +78,7 @@ SIGNATURES = {
     "gr_acq_run_dev": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P]),
     "gr_acq_run_host": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P]),
     "gr_acq_last_launches": (C.c_int, [_P]),
+    "gr_acq_last_inverse_form": (C.c_int, [_P]),
     "gr_acq_search_dev": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P]),
     "gr_acq_search_host": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P]),
     "gr_synth_iq_dev": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, C.c_float, C.c_uint64, _P]),

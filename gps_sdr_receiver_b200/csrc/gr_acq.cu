@@ -47,6 +47,7 @@ struct gr_acq_plan {
     cudaEvent_t ev_in[GR_ACQ_HOST_CHUNKS];
     bool pipe_ready;
     int last_launches;
+    int last_inv_form;                            // GR_ACQ_INV_4CTA / GR_ACQ_INV_QUAD of the last run's inverse launches
     // The scratch above (d_spec, d_cells) belongs to the plan, so two *_dev calls of one plan must not overlap: a call on
     // another stream than the previous one first makes its stream wait for the event recorded behind the previous call.
     cudaEvent_t ev_last;
@@ -257,7 +258,9 @@ __device__ __forceinline__ float sel16(const float* st, int j) {
     for (int q = 1; q < 16; ++q) v = (j == q) ? st[q] : v;
     return v;
 }
-__device__ __forceinline__ void acq_cell_epilogue(const float* st, int nb, int t, gr_acq_cell* cell, AcqScratch* S) {
+template <int BAR = 0>      // BAR = 0: the block barrier; else named barrier BAR over 128 threads (one group of a larger CTA)
+__device__ __forceinline__ void acq_cell_epilogue(const float* st, int nb, int t, gr_acq_cell* cell, AcqScratch* S, int bar_id = 0) {
+    auto sync = [&]() { if (BAR == 0) __syncthreads(); else asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
     float s = 0.f, s2 = 0.f, m1 = -1.f, m2 = -1.f;
     int j1 = 0;
 #pragma unroll
@@ -279,7 +282,7 @@ __device__ __forceinline__ void acq_cell_epilogue(const float* st, int nb, int t
     const int widx = (int)__reduce_min_sync(0xffffffffu, __float_as_uint(m1) == wmax ? (unsigned)(nb + 128 * j1) : 0x7fffffffu);
     const int w = t >> 5;
     if ((t & 31) == 0) { S->d[w] = (double)s; S->d[4 + w] = (double)s2; S->f[w] = __uint_as_float(wmax); S->i[w] = widx; }
-    __syncthreads();
+    sync();
     float peak = S->f[0];
     int mx = S->i[0];
 #pragma unroll
@@ -298,7 +301,7 @@ __device__ __forceinline__ void acq_cell_epilogue(const float* st, int nb, int t
     const int lo = (mx + GR_N - 1) & (GR_N - 1), hi = (mx + 1) & (GR_N - 1);
     if (((lo - nb) & 127) == 0) cell->em1 = sel16(st, ((lo - nb) & (GR_N - 1)) >> 7);
     if (((hi - nb) & 127) == 0) cell->ep1 = sel16(st, ((hi - nb) & (GR_N - 1)) >> 7);
-    __syncthreads();
+    sync();
     if (t == 64) {                                   // not warp 0: that one issues the TMA loads
         const double sum = (S->d[0] + S->d[1]) + (S->d[2] + S->d[3]), sum2 = (S->d[4] + S->d[5]) + (S->d[6] + S->d[7]);
         const double mean = sum * (1.0 / GR_N);
@@ -746,6 +749,253 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base_sh), "r"(kAlloc));
 }
 
+// ---- kernel 2, "quad" form: one 512-thread CTA per SM = four 128-thread groups sharing the forward spectrum ----------
+// The four groups work on four PRNs of the SAME (recording, Doppler bin) and consume the same spectra X_k: one TMA fill of a
+// double-buffered stage serves four transforms (a quarter of the TMA writes into shared memory and of the L2 reads of the
+// 4-CTA form), and it is issued by whichever warp is the LAST to have read the previous contents (an acq_rel counter in
+// shared memory: nobody waits for the stage to become empty, no fixed warp is the straggler).  Groups synchronise among
+// themselves only through the stage (a group can run up to two transforms ahead of the slowest); inside a group everything
+// is as in acq_inv_kernel with named barriers in place of the block barrier.  Twiddles sit in TMEM once per CTA (lanes are
+// shared by warps w, w + 4, ...); 64 + 4 x 64 = 320 of the SM's 512 columns.
+#define GR_ACQ_QUAD_SMEM(NS) (4 * 2 * GR_W_BUF1_BYTES + (NS) * GR_W_BUF1_BYTES)      // 4 x double exchange-1 buffer + NS stages (NS = 4: 192 KiB)
+template <int NS>      // stages of the forward-spectrum ring (a power of two)
+__global__ void __launch_bounds__(512, 1) acq_inv_quad_kernel(const AcqArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t xfull[NS];       // stage i holds its spectrum (TMA completion)
+    __shared__ __align__(8) uint64_t xempty[NS];      // all 16 warps have read stage i
+    constexpr int kLog = NS == 2 ? 1 : NS == 4 ? 2 : 3;
+    static_assert((1 << kLog) == NS, "NS must be 2, 4 or 8");
+    __shared__ AcqScratch scratch[4];
+    __shared__ uint32_t tm_base_sh;
+    constexpr int kAlloc = 512;
+    constexpr int kColTw2 = 0, kColTw1 = 32;
+
+    const int tid = threadIdx.x;
+    const int t = tid & 127;                                    // thread of the group = FFT thread
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // 0..15, warp-uniform for the compiler
+    const int g = warp >> 2;                                    // group 0..3
+    const int bar_id = 1 + g;
+    const int kColC = 64 + 64 * g, kColX = 96 + 64 * g;
+    unsigned char* gsm = smem_raw + (size_t)g * (2 * GR_W_BUF1_BYTES);           // this group's two exchange-1 buffers
+    float4* buf1 = reinterpret_cast<float4*>(gsm);
+    unsigned char* stage0 = smem_raw + 4 * 2 * GR_W_BUF1_BYTES;                  // stage b at stage0 + b * 16 KiB
+    const int nunits = a.nrec * a.nbins;
+    const int nrounds = (a.nprn + 3) >> 2;
+    const int per_unit = nrounds * a.nnoncoh;                   // stage fills per unit
+    const int my_units = ((int)blockIdx.x < nunits) ? (nunits - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nseq = my_units * per_unit;                       // stage fills of this CTA
+
+    if (tid == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 16); }
+    }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(&tm_base_sh)), "r"(kAlloc));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tm = tm_base_sh + ((uint32_t)(32 * (warp & 3)) << 16);
+
+    constexpr size_t kStrideK = 2 * (size_t)GR_N * 8;                            // bytes between intervals
+    auto prn_of = [&](int i) -> int { return a.in_params ? a.prn_c[i] : a.prns[i]; };
+    // source of stage fill number q of this CTA: unit blockIdx.x + (q / per_unit) gridDim.x, interval (q % per_unit) % nnoncoh
+    auto fill_src = [&](int q, int& rot_out) -> const char* {
+        const int unit = (int)blockIdx.x + (q / per_unit) * (int)gridDim.x;
+        const int k = (q % per_unit) % a.nnoncoh;
+        const int b = unit % a.nbins, r = unit / a.nbins;
+        const int code = a.in_params ? a.bin_c[b] : ((a.bin_base[b] << 16) | a.bin_shift[b]);
+        const int sh = code & 0xffff;
+        rot_out = sh & ~1;
+        return reinterpret_cast<const char*>(a.spec) + ((size_t)(r * a.nbase + (code >> 16)) * a.nnoncoh * 2 + (sh & 1)) * (GR_N * 8) +
+               (size_t)k * kStrideK;
+    };
+    if (tid == 0) {
+        for (int q = 0; q < NS && q < nseq; ++q) {
+            int rot;
+            const char* src = fill_src(q, rot);
+            tma_load_rot(stage0 + q * GR_W_BUF1_BYTES, src, rot, &xfull[q]);
+        }
+    }
+    {
+        float w[32];
+        if (g == 0) {                                            // twiddles, once per CTA (TMEM lanes are shared across the groups)
+            const int L = t & 31;
+            const int k1 = 4 * (t >> 5) + 2 * (L >> 4) + (L & 1), n3 = (L >> 1) & 7;
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const float2 u = a.tab.tw1[(8 * n2 + n3) * 16 + k1];
+                const int j0 = n2 & 3, m = n2 >> 2, q = 16 * (j0 >> 1) + 2 * (4 * (j0 & 1) + m);
+                w[q] = u.x; w[q + 1] = u.y;
+            }
+            tm_st16(tm + kColTw1, w);
+            tm_st16(tm + kColTw1 + 16, w + 16);
+            const int k2lo = 4 * ((L >> 2) & 1) + 2 * ((L >> 4) & 1) + ((L >> 1) & 1);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int n = 1; n < 8; ++n) {
+                    const float2 u = a.tab.tw2[n * 16 + k2lo + 8 * h];
+                    w[16 * h + 2 * (n - 1)] = u.x; w[16 * h + 2 * (n - 1) + 1] = u.y;
+                }
+                w[16 * h + 14] = 0.f; w[16 * h + 15] = 0.f;
+            }
+            tm_st16(tm + kColTw2, w);
+            tm_st16(tm + kColTw2 + 16, w + 16);
+        }
+        if (my_units > 0 && g < a.nprn) {                        // first job's conjugate code spectrum
+            load_conjspec<true>(w, a.tab.conjspec + (size_t)prn_of(g) * GR_N + t);
+            tm_st16(tm + kColC, w);
+            tm_st16(tm + kColC + 16, w + 16);
+        }
+        tm_wait_st();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    const float sc = (a.mode == GR_ACQ_POW) ? a.scale * a.scale : a.scale;
+    const int obase = fftt_out_base(t);
+    int par = 0;                       // exchange-1 buffer of this group's next transform
+    int seq = 0;                       // stage fills consumed so far (all warps of the CTA count alike)
+
+    for (int u = 0; u < my_units; ++u) {
+        const int unit = (int)blockIdx.x + u * (int)gridDim.x;
+        const int bin = unit % a.nbins, rec = unit / a.nbins;
+        for (int r = 0; r < nrounds; ++r) {
+            const int pi = 4 * r + g;                            // this group's PRN of the round
+            const bool active = pi < a.nprn;
+            // the job after this one of this group: its PRN of the next round, or (none left in this unit) of the next unit's round 0
+            int n_pi = pi + 4;
+            bool has_next = true;
+            if (n_pi >= a.nprn) { n_pi = g; has_next = u + 1 < my_units; }
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+            // this warp is done with the stage of fill sq
+            auto release_stage = [&](int sq) {
+                __syncwarp();
+                if ((tid & 31) == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(&xempty[sq & (NS - 1)])) : "memory");
+            };
+            // Refill: at the top of fill sq, warp (sq mod 16) refills the stage that was read two fills ago (every warp has almost
+            // certainly released it by now) with the spectrum NS - 2 fills ahead.  The duty rotates over the 16 warps: a fixed
+            // issuer -- or the last warp to release a stage, which is by construction the slowest -- would carry the ~300 cycles
+            // of address arithmetic and TMA issue on every transform and hold its whole group back at the next barrier.
+            auto refill = [&](int sq) {
+                const int tgt = sq - 2 + NS;
+                if (warp == (sq & 15) && sq >= 2 && tgt < nseq) {
+                    if (elect_one()) {
+                        const int eb = (sq - 2) & (NS - 1);
+                        mbar_wait(&xempty[eb], ((sq - 2) >> kLog) & 1);
+                        int rot;
+                        const char* src = fill_src(tgt, rot);
+                        tma_load_rot(stage0 + eb * GR_W_BUF1_BYTES, src, rot, &xfull[eb]);
+                    }
+                    __syncwarp();
+                }
+            };
+            if (!active) {                                       // a group without a PRN in this round only keeps the stage protocol going
+                for (int k = 0; k < a.nnoncoh; ++k, ++seq) {
+                    refill(seq);
+                    mbar_wait(&xfull[seq & (NS - 1)], (seq >> kLog) & 1);
+                    release_stage(seq);
+                }
+                continue;
+            }
+            for (int k = 0; k < a.nnoncoh; ++k, ++seq) {
+                const int sb = seq & (NS - 1);
+                const float2* xs = reinterpret_cast<const float2*>(stage0 + sb * GR_W_BUF1_BYTES);
+                cpk y[16];
+                float cl[16], ch[16];
+                tm_ld16_issue(tm + kColC, cl);
+                tm_ld16_issue(tm + kColC + 16, ch);
+                refill(seq);
+                mbar_wait(&xfull[sb], (seq >> kLog) & 1);
+                // conj(X_j) in butterfly order; the two halves of the first butterfly layer one after the other
+                {
+                    float xl[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int j0 = j & 3, m = j >> 2, q = 2 * (4 * (j0 & 1) + m);
+                        if (!(j0 >> 1)) { const float2 v = xs[t + 128 * j]; xl[q] = v.x; xl[q + 1] = -v.y; }
+                    }
+                    tm_ld_wait16(cl);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int j0 = j & 3, m = j >> 2, q = 2 * (4 * (j0 & 1) + m);
+                        if (!(j0 >> 1)) y[j] = cpk_make(cl[q], cl[q + 1]);
+                    }
+                    cpk_dft16_in_tw<0>(y, xl);
+                }
+                {
+                    float xh[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int j0 = j & 3, m = j >> 2, q = 2 * (4 * (j0 & 1) + m);
+                        if (j0 >> 1) { const float2 v = xs[t + 128 * j]; xh[q] = v.x; xh[q + 1] = -v.y; }
+                    }
+                    tm_ld_wait16(ch);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int j0 = j & 3, m = j >> 2, q = 2 * (4 * (j0 & 1) + m);
+                        if (j0 >> 1) y[j] = cpk_make(ch[q], ch[q + 1]);
+                    }
+                    release_stage(seq);                          // X_k is in registers
+                    cpk_dft16_in_tw<2>(y, xh);
+                }
+                cpk_dft16_out(y);
+                float4* b1 = buf1 + par * (GR_W_BUF1_BYTES / 16);
+                par ^= 1;
+                fftt_ex1_write_pk(b1, t, y);
+                float wa[16], wb[16];
+                tm_ld16_issue(tm + kColTw1, wa);                 // arrives while the group waits at its barrier
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (k + 1 == a.nnoncoh && has_next) {
+                    // next job's conjugate code spectrum: global -> this thread's private slots of the group's idle exchange buffer
+                    const float2* cs = a.tab.conjspec + (size_t)prn_of(n_pi) * GR_N + t;
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(gsm + par * GR_W_BUF1_BYTES) + t * 8;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 1024 * j), "l"(cs + 128 * j) : "memory");
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+                fftt_ex1_read_pk(b1, t, y);
+                tm_ld_wait16(wa);
+                tm_ld16_issue(tm + kColTw1 + 16, wb);
+                cpk_dft16_in_tw<0>(y, wa);
+                tm_ld_wait16(wb);
+                cpk_dft16_in_tw<2>(y, wb);
+                cpk_dft16_out(y);
+                fftt_ex2_stage3_pk(tm + kColX, tm + kColTw2, y);
+                if (a.mode == GR_ACQ_POW) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { float yr, yi; cpk_split(y[j], yr, yi); acc[j] = fmaf(yr, yr, fmaf(yi, yi, acc[j])); }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { float yr, yi; cpk_split(y[j], yr, yi); acc[j] += sqrtf(yr * yr + yi * yi); }
+                }
+            }
+            if (has_next) {
+                float w[32];
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                conjspec_from_smem<true>(w, reinterpret_cast<const float2*>(gsm + par * GR_W_BUF1_BYTES) + t);
+                tm_st16(tm + kColC, w);
+                tm_st16(tm + kColC + 16, w + 16);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] *= sc;
+            acq_cell_epilogue<1>(acc, obase, t, a.out + ((size_t)rec * a.nprn + pi) * a.nbins + bin, &scratch[g], bar_id);
+            if (has_next) tm_wait_st();
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base_sh), "r"(kAlloc));
+}
+
 // ------------------------------------------------------------------------------------------
 #define GR_ACQ_G 4
 
@@ -786,7 +1036,7 @@ extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* b
         if (prns[i] < 1 || prns[i] > GR_MAX_PRN) { gr_set_error("gr_acq_plan_create: prn %d out of range", prns[i]); return GR_ERR_ARG; }
     gr_acq_plan* p = new gr_acq_plan();
     p->nprn = nprn; p->nbins = nbins; p->tcoh = tcoh_ms; p->nnoncoh = nnoncoh; p->mode = mode; p->in_format = in_format;
-    p->d_in = nullptr; p->in_bytes = 0; p->d_out = nullptr; p->out_bytes = 0; p->last_launches = 0;
+    p->d_in = nullptr; p->in_bytes = 0; p->d_out = nullptr; p->out_bytes = 0; p->last_launches = 0; p->last_inv_form = GR_ACQ_INV_4CTA;
     p->d_cells = nullptr; p->cells_bytes = 0; p->d_best = nullptr; p->best_bytes = 0;
     p->d_spec = nullptr; p->spec_bytes = 0;
     p->pipe_ready = false;
@@ -855,6 +1105,7 @@ extern "C" int gr_acq_plan_destroy(gr_acq_plan* p) {
 }
 
 extern "C" int gr_acq_last_launches(const gr_acq_plan* p) { return p ? p->last_launches : 0; }
+extern "C" int gr_acq_last_inverse_form(const gr_acq_plan* p) { return p ? p->last_inv_form : GR_ACQ_INV_4CTA; }
 extern "C" int gr_acq_plan_form(const gr_acq_plan* p) { return p && p->exact_nco ? GR_ACQ_FORM_EXACT : GR_ACQ_FORM_FAST; }
 
 static int grow(void** ptr, size_t* have, size_t need) {
@@ -891,14 +1142,16 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
                                                             : (one ? acq_fwd_kernel<GR_IN_CF32, true> : acq_fwd_kernel<GR_IN_CF32, false>);
     // development switch: GPSB200_ACQ_SCALAR=1 selects the scalar-FP32 form of the same transform (A/B timing)
     static const bool scalar_fp = getenv("GPSB200_ACQ_SCALAR") != nullptr;
-    void (*inv)(const AcqArgs) = scalar_fp ? acq_inv_kernel<GR_ACQ_G, 6, 4, false> : acq_inv_kernel<GR_ACQ_G, 6, 4, true>;
+    // PRNs per work item of the 4-CTA form: 4, or 2 / 1 where smaller items shorten the last wave of a small launch (below)
+    void (*const inv_by_g[3])(const AcqArgs) = {acq_inv_kernel<1, 6, 4, true>, acq_inv_kernel<2, 6, 4, true>,
+                                                scalar_fp ? acq_inv_kernel<GR_ACQ_G, 6, 4, false> : acq_inv_kernel<GR_ACQ_G, 6, 4, true>};
     const size_t fwd_smem = GR_FFT_SMEM_BYTES + (one ? 0 : (size_t)p->tcoh * sizeof(cf));
     if (fwd_smem > 200 * 1024) { gr_set_error("gr_acq_run_dev: tcoh too large"); return GR_ERR_ARG; }
     GR_CUDA(cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
     // development switch: GPSB200_ACQ_CTAS=2|3 pads the dynamic shared memory so that fewer CTAs fit an SM (occupancy study)
     static const int ctas_per_sm = getenv("GPSB200_ACQ_CTAS") ? atoi(getenv("GPSB200_ACQ_CTAS")) : 4;
     const int inv_smem = ctas_per_sm == 3 ? 72 * 1024 : ctas_per_sm == 2 ? 110 * 1024 : ctas_per_sm == 1 ? 200 * 1024 : GR_ACQ_INV_SMEM;
-    GR_CUDA(cudaFuncSetAttribute(inv, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem));
+    for (int i = 0; i < 3; ++i) GR_CUDA(cudaFuncSetAttribute(inv_by_g[i], cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem));
     const size_t bps = p->in_format == GR_IN_U8IQ ? 2 : 8;
     p->last_launches = 0;
     for (int r0 = 0; r0 < nrec; r0 += sub) {
@@ -922,7 +1175,24 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         a.nrec = nr;
         a.nprn = p->nprn;
         a.nbins = p->nbins;
-        a.ngroups = (p->nprn + GR_ACQ_G - 1) / GR_ACQ_G;
+        // Work items of the 4-CTA form = (recording, bin, G PRNs), G x nnoncoh transforms each, dealt round-robin to the resident
+        // CTAs: the launch lasts ceil(items / CTAs) items.  G = 4 unless smaller items shorten that (each item costs about a
+        // quarter of a transform on top: work-item change): e.g. a 51-bin shard of configs[3] on 16 recordings is 12 rounds of
+        // 80 transforms at G = 4 and 45 rounds of 20 at G = 1 (6 % less).
+        const long long n_cta = (long long)(ctas_per_sm >= 1 && ctas_per_sm <= 4 ? ctas_per_sm : 4) * gr_lib()->num_sms;
+        int gsel = GR_ACQ_G;
+        double t_std = 0.0;
+        for (int gg = GR_ACQ_G; gg >= 1; gg >>= 1) {
+            const long long items = (long long)nr * p->nbins * ((p->nprn + gg - 1) / gg);
+            const double tg = (double)((items + n_cta - 1) / n_cta) * ((double)(gg * p->nnoncoh) + 0.25);
+            if (gg == GR_ACQ_G || tg < 0.99 * t_std) { gsel = gg; t_std = tg; }
+        }
+        if (const char* g_env = getenv("GPSB200_ACQ_G")) {            // GPSB200_ACQ_G=1|2|4 forces the item size (read per call: the tests flip it)
+            const int gg = atoi(g_env);
+            if (gg == 1 || gg == 2 || gg == 4) gsel = gg;
+        }
+        if (scalar_fp) gsel = GR_ACQ_G;
+        a.ngroups = (p->nprn + gsel - 1) / gsel;
         a.tcoh = p->tcoh;
         a.nnoncoh = p->nnoncoh;
         a.mode = p->mode;
@@ -941,9 +1211,29 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         const long long ninv = (long long)nr * p->nbins * a.ngroups;
         if (nfwd > 0x7fffffffLL || ninv > 0x7fffffffLL) { gr_set_error("gr_acq_run_dev: grid too large"); return GR_ERR_ARG; }
         fwd<<<(unsigned)nfwd, GR_FFT_THREADS, fwd_smem, s>>>(a);
-        const long long resident = (long long)(ctas_per_sm >= 1 && ctas_per_sm <= 4 ? ctas_per_sm : 4) * gr_lib()->num_sms;
-        const long long ninv_grid = ninv < resident ? ninv : resident;
-        inv<<<(unsigned)ninv_grid, GR_FFT_THREADS, inv_smem, s>>>(a);
+        // Form of the inverse kernel: the quad form (one 512-thread CTA per SM, four PRNs of a (recording, bin) unit sharing
+        // the staged spectra) is 4 - 5 % faster per transform on full launches (21.3 against 22.4 ms per 512 recordings,
+        // 5.41 against 5.63 ms per 128: gpurun_out/r02_quad_ab.log) but hands out work in units of all PRNs x all intervals;
+        // the 4-CTA form in items of 4 PRNs.  Pick the one with the shorter critical path in transform slots (the last wave
+        // of a small launch decides: 16 recordings 0.73 against 0.77 ms, 4 recordings 0.19 against 0.31 ms for the 4-CTA
+        // form); GPSB200_ACQ_QUAD=0 / 1 forces a form.
+        const char* quad_env = getenv("GPSB200_ACQ_QUAD");           // read per call: the tests flip it
+        const long long nunits = (long long)nr * p->nbins;
+        const long long sms = gr_lib()->num_sms;
+        const long long nrounds = (p->nprn + 3) / 4;
+        const double t_quad = (double)((nunits + sms - 1) / sms) * (double)(nrounds * p->nnoncoh) * 0.95;
+        const bool quad = quad_env ? atoi(quad_env) != 0 : (ctas_per_sm == 4 && t_quad < t_std);
+        p->last_inv_form = quad ? GR_ACQ_INV_QUAD : GR_ACQ_INV_4CTA;
+        if (quad) {
+            const long long qgrid = nunits < sms ? nunits : sms;
+            void (*qk)(const AcqArgs) = acq_inv_quad_kernel<4>;
+            const int qsmem = GR_ACQ_QUAD_SMEM(4);
+            GR_CUDA(cudaFuncSetAttribute(qk, cudaFuncAttributeMaxDynamicSharedMemorySize, qsmem));
+            qk<<<(unsigned)qgrid, 512, qsmem, s>>>(a);
+        } else {
+        const long long ninv_grid = ninv < n_cta ? ninv : n_cta;
+        inv_by_g[gsel == 1 ? 0 : gsel == 2 ? 1 : 2]<<<(unsigned)ninv_grid, GR_FFT_THREADS, inv_smem, s>>>(a);
+        }
         GR_CUDA(cudaGetLastError());
         p->last_launches += 2;
     }

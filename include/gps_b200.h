@@ -106,6 +106,14 @@ int gr_acq_run_host(gr_acq_plan* plan, const void* h_samples, int nrec, int64_t 
                     gr_acq_cell* h_out);
 /* kernel launches issued by the last run of this plan (for bench accounting) */
 int gr_acq_last_launches(const gr_acq_plan* plan);
+/* Form of the inverse kernel the last run launched.  Both compute the same cells bit for bit; the launcher picks per call:
+ * GR_ACQ_INV_4CTA = acq_inv_kernel, four 128-thread CTAs per SM, work handed out in items of 4 PRNs x all intervals;
+ * GR_ACQ_INV_QUAD = acq_inv_quad_kernel, one 512-thread CTA per SM whose four groups share every staged forward spectrum,
+ * work handed out per (recording, bin): faster on launches that fill the GPU many times over, slower on small ones.
+ * Environment (read per call): GPSB200_ACQ_QUAD=0 / =1 forces a form. */
+#define GR_ACQ_INV_4CTA 0
+#define GR_ACQ_INV_QUAD 1
+int gr_acq_last_inverse_form(const gr_acq_plan* plan);
 
 /* The search result proper: for every recording and PRN the Doppler bin with the largest
  * z (first maximum), i.e. the (PRN, Doppler, code-phase, metric) tuple.  The full cell grid

@@ -315,6 +315,40 @@ def test_full_size_config4_grid_vs_oracle_both_forms(gpu, monkeypatch):
             assert abs(bins[ob] - s_.doppler) <= 50.0 and (int(b["cell"]["mx"]) - int(s_.delay)) % 2048 in (0, 1)
 
 
+def test_quad_form_of_the_inverse_kernel_equals_the_4cta_form_bit_for_bit(gpu, monkeypatch):
+    """The launcher picks between two forms of the inverse kernel (gr_acq_run_dev): 4 CTAs of 128 threads per SM, or one
+    512-thread CTA whose four groups share the staged forward spectra.  Same arithmetic per (recording, bin, PRN): the cells
+    are bit-identical.  Forced here on grids the launcher would not give to the quad form: a PRN count that is not a
+    multiple of 4 (groups idle in the last round), fewer units than SMs, one non-coherent interval, both statistics."""
+    from gps_sdr_receiver_b200 import synth
+    from gps_sdr_receiver_b200.acquisition import AcqPlan, GR_ACQ_ABS, GR_ACQ_POW
+    sats = [synth.Sat(prn=3, doppler=2440.0, delay=133.4, amp=0.1), synth.Sat(prn=30, doppler=-1990.0, delay=0.2, amp=0.1)]
+    for prns, bins, tcoh, k, mode, nrec in (
+            (list(range(1, 31)), [-3000.0 + 500.0 * b for b in range(13)], 1, 3, GR_ACQ_POW, 3),
+            ([3, 30, 7], [2400.0, -2000.0], 2, 1, GR_ACQ_ABS, 1),
+            (list(range(1, 33)), [-10000.0 + 500.0 * b for b in range(41)], 1, 10, GR_ACQ_POW, 5)):
+        raw = synth.make_iq(sats, nrec * tcoh * k, seed=31)
+        out = {}
+        for quad in ("0", "1"):
+            monkeypatch.setenv("GPSB200_ACQ_QUAD", quad)
+            plan = AcqPlan(prns, bins, tcoh, k, mode)
+            out[quad] = plan.run(raw, nrec=nrec)
+            plan.close()
+        monkeypatch.setenv("GPSB200_ACQ_QUAD", "0")
+        for gsz in ("1", "2"):                                  # the 4-CTA form with 1 or 2 PRNs per work item (small launches)
+            monkeypatch.setenv("GPSB200_ACQ_G", gsz)
+            plan = AcqPlan(prns, bins, tcoh, k, mode)
+            out["g" + gsz] = plan.run(raw, nrec=nrec)
+            assert plan.inverse_kernel() == "acq_inv_kernel"
+            plan.close()
+        monkeypatch.delenv("GPSB200_ACQ_G")
+        monkeypatch.delenv("GPSB200_ACQ_QUAD")
+        assert out["0"].tobytes() == out["1"].tobytes(), (len(prns), len(bins), tcoh, k)
+        assert out["0"].tobytes() == out["g1"].tobytes() and out["0"].tobytes() == out["g2"].tobytes(), (len(prns), len(bins), tcoh, k)
+        c = out["1"]
+        assert int(c["mx"][0, prns.index(3), int(np.argmax(c["z"][0, prns.index(3)]))]) in (133, 134)
+
+
 def test_ragged_and_invalid_inputs(gpu):
     from gps_sdr_receiver_b200 import _capi
     from gps_sdr_receiver_b200.acquisition import AcqPlan
