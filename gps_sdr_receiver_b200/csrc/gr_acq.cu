@@ -180,18 +180,27 @@ __global__ void __launch_bounds__(GR_FFT_THREADS) acq_fwd_kernel(const AcqArgs a
                 const float w32b = two ? a.w32[bin + 1] : w32;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { X[j] = cf{0.f, 0.f}; Y[j] = cf{0.f, 0.f}; }
+                // The argument arithmetic runs on the packed instructions (gr_cpk.cuh: lane by lane the operations of tsec_of /
+                // nco_fast2, bit-identical results): the time values of two samples per instruction, then the arguments of the
+                // two bins per instruction -- this kernel is bound by its issue slots, not by the FP32 pipe.
+                const cpk w2 = cpk_make(w32, w32b);
                 float fn0 = (float)(base0 + 1);                    // n + 1 of this thread's first sample of block i (exact: < 2^24)
                 for (int i = 0; i < a.tcoh; ++i, fn0 += (float)GR_N) {
+                    const cpk fnp = cpk_make(fn0, fn0 + 128.0f);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const cf x = load_sample<IN_FMT>(src, base0 + (long long)i * GR_N + 128 * j);
-                        const float ts = tsec_of(fn0 + (float)(128 * j));
-                        const cf e = nco_fast2(__fmul_rn(w32, ts));
-                        const cf f = nco_fast2(__fmul_rn(w32b, ts));
-                        X[j].x = fmaf(x.x, e.x, X[j].x); X[j].x = fmaf(-x.y, e.y, X[j].x);
-                        X[j].y = fmaf(x.y, e.x, X[j].y); X[j].y = fmaf(x.x, e.y, X[j].y);
-                        Y[j].x = fmaf(x.x, f.x, Y[j].x); Y[j].x = fmaf(-x.y, f.y, Y[j].x);
-                        Y[j].y = fmaf(x.y, f.x, Y[j].y); Y[j].y = fmaf(x.x, f.y, Y[j].y);
+                    for (int j = 0; j < 16; j += 2) {
+                        float ts[2];
+                        cpk_split(tsec_of2(cpk_add(fnp, cpk_bc((float)(128 * j)))), ts[0], ts[1]);
+#pragma unroll
+                        for (int o = 0; o < 2; ++o) {
+                            const cf x = load_sample<IN_FMT>(src, base0 + (long long)i * GR_N + 128 * (j + o));
+                            cf e, f;
+                            nco_fast2_pair(cpk_mul(w2, cpk_bc(ts[o])), e, f);
+                            X[j + o].x = fmaf(x.x, e.x, X[j + o].x); X[j + o].x = fmaf(-x.y, e.y, X[j + o].x);
+                            X[j + o].y = fmaf(x.y, e.x, X[j + o].y); X[j + o].y = fmaf(x.x, e.y, X[j + o].y);
+                            Y[j + o].x = fmaf(x.x, f.x, Y[j + o].x); Y[j + o].x = fmaf(-x.y, f.y, Y[j + o].x);
+                            Y[j + o].y = fmaf(x.y, f.x, Y[j + o].y); Y[j + o].y = fmaf(x.x, f.y, Y[j + o].y);
+                        }
                     }
                 }
             } else {

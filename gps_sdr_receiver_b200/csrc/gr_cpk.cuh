@@ -138,4 +138,30 @@ __device__ __forceinline__ void cpk_dft8_tw(cpk* a, const float* w) {
     cpk_bf4_w123(a[1], a[3], a[5], a[7], w[4], w[5], w[8], w[9], w[12], w[13]);
     cpk_dft8_out(a);
 }
+// ---- the reference's NCO for TWO consecutive samples on the packed instructions -------------------------------------
+// fn = (n + 1, n + 2) as floats.  Lane by lane the same IEEE operations in the same order as nco_exact (gr_common.cuh):
+// bit-identical factors, half the issue slots for the nine argument instructions (the two MUFU per sample stay scalar).
+__device__ __forceinline__ cpk cpk_bc(float v) { return cpk_make(v, v); }
+// exp(-i arg) for the two halves of `arg` (nco_fast2 twice)
+__device__ __forceinline__ void nco_fast2_pair(cpk arg, cf& e0, cf& e1) {
+    const cpk k = cpk_add(cpk_fma(arg, cpk_bc(0.15915494309189535f), cpk_bc(12582912.0f)), cpk_bc(-12582912.0f));
+    cpk r = cpk_fma(k, cpk_bc(-6.28125f), arg);
+    r = cpk_fma(k, cpk_bc(-1.9353071795864769e-3f), r);
+    float r0, r1;
+    cpk_split(r, r0, r1);
+    e0 = cf{__cosf(r0), -__sinf(r0)};
+    e1 = cf{__cosf(r1), -__sinf(r1)};
+}
+// (tsec_of(k0), tsec_of(k1)) for fn = (k0, k1)
+__device__ __forceinline__ cpk tsec_of2(cpk fn) {
+    return cpk_fma(fn, cpk_bc(__uint_as_float(889393775u)), cpk_mul(fn, cpk_bc(__uint_as_float(2832262496u))));
+}
+// fl32(phase + fl32(w t)) needs the product ROUNDED before the addition.  ptxas contracts `mul.rn.f32x2` + `add.rn.f32x2`
+// into one FFMA2 (seen in the SASS; it even rewrites fma(p, 1, phase) into that), which silently drops the rounding --
+// the scalar `add.rn.f32` is never contracted, so the two additions are scalar.
+__device__ __forceinline__ void nco_exact2(float w32, float phase32, cpk fn, cf& e0, cf& e1) {
+    float p0, p1;
+    cpk_split(cpk_mul(cpk_bc(w32), tsec_of2(fn)), p0, p1);
+    nco_fast2_pair(cpk_make(__fadd_rn(phase32, p0), __fadd_rn(phase32, p1)), e0, e1);
+}
 #endif

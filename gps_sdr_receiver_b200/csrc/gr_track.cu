@@ -334,7 +334,6 @@ __device__ __forceinline__ void fold_blocks(cf* F, const void* src, int first, i
 // integer-valued floats) and two FFMA2 (complex multiply-accumulate), against one LDS.U16, two PRMT, two FADD, four FFMA
 // and address / select work in the scalar form (ncu, profiles/track_r01_v5_regions.txt: 115 IADD3 + 100 FSEL + 96 PRMT per
 // 126 FFMA in the prompt pass).
-__device__ __forceinline__ cpk cpk_bc(float v) { return cpk_make(v, v); }
 __device__ __forceinline__ void load8_u8(const unsigned char* p, cpk* x) {
     const uint4 v = *reinterpret_cast<const uint4*>(p);
     const cpk magic = cpk_make(-8388608.0f, -8388608.0f);
@@ -769,14 +768,19 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                                 cpk x[8];
                                 load8_u8(pb + 16 * uh, x);
                                 const float f0 = (float)(b * GR_N + 8 * uh + 1);
+                                const cpk fn0 = cpk_make(f0, f0 + 1.0f);
                                 cpk s0 = cpk_make(0.f, 0.f), s1 = s0;
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const cf e = nco_exact(w32, phase32, f0 + (float)i);
-                                    const cpk y = cpk_cmul(true_sample_pk(x[i]), e.x, e.y);
-                                    if (kFold) A[8 * h + i] = cpk_add(A[8 * h + i], y);
-                                    const cpk c2 = cpk_make(cc[8 * h + i], cc[8 * h + i]);
-                                    if (i & 1) s1 = cpk_fma(y, c2, s1); else s0 = cpk_fma(y, c2, s0);
+                                for (int i = 0; i < 8; i += 2) {
+                                    cf e[2];
+                                    nco_exact2(w32, phase32, cpk_add(fn0, cpk_bc((float)i)), e[0], e[1]);   // samples i, i + 1
+#pragma unroll
+                                    for (int o = 0; o < 2; ++o) {
+                                        const cpk y = cpk_cmul(true_sample_pk(x[i + o]), e[o].x, e[o].y);
+                                        if (kFold) A[8 * h + i + o] = cpk_add(A[8 * h + i + o], y);
+                                        const cpk c2 = cpk_make(cc[8 * h + i + o], cc[8 * h + i + o]);
+                                        if (o) s1 = cpk_fma(y, c2, s1); else s0 = cpk_fma(y, c2, s0);
+                                    }
                                 }
                                 float re, im;
                                 cpk_split(cpk_add(s0, s1), re, im);
@@ -956,11 +960,13 @@ __global__ void __launch_bounds__(NT, kDense ? 3 : 1) track_kernel(const TrackAr
                             const float f1 = (float)((v1 ? b1 : 0) * GR_N + 8 * u1 + 1);
 #pragma unroll
                             for (int i = 0; i < 8; i += 2) {
-                                const cf e0 = nco_exact(w32, phase32, f0 + (float)i), e1 = nco_exact(w32, phase32, f0 + (float)(i + 1));
+                                cf e0, e1;
+                                nco_exact2(w32, phase32, cpk_add(cpk_make(f0, f0 + 1.0f), cpk_bc((float)i)), e0, e1);
                                 a0 = cpk_mac(a0, true_sample_pk(x[i]), e0.x * qr[i], e0.y * qr[i]);
                                 b0e = cpk_mac(b0e, true_sample_pk(x[i + 1]), e1.x * qr[i + 1], e1.y * qr[i + 1]);
                                 if (NC == 2) {
-                                    const cf g0 = nco_exact(w32, phase32, f1 + (float)i), g1 = nco_exact(w32, phase32, f1 + (float)(i + 1));
+                                    cf g0, g1;
+                                    nco_exact2(w32, phase32, cpk_add(cpk_make(f1, f1 + 1.0f), cpk_bc((float)i)), g0, g1);
                                     a1 = cpk_mac(a1, true_sample_pk(y[i]), g0.x * qr[8 * (NC - 1) + i], g0.y * qr[8 * (NC - 1) + i]);
                                     b1e = cpk_mac(b1e, true_sample_pk(y[i + 1]), g1.x * qr[8 * (NC - 1) + i + 1], g1.y * qr[8 * (NC - 1) + i + 1]);
                                 }
