@@ -404,12 +404,14 @@ def run_b200(args):
         "gpu_launches": launches,
         "roofline": {"bound": "fp32", "kernel": inv_kernel_name + " (+ acq_fwd_kernel, 0.5 % of the launch pair)", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp32_peak,
-                     # dram__bytes_read + dram__bytes_write of the kernel pair, ncu --set full capture of 128 recordings
-                     # (profiles/acq_r01_v8_ncu_summary.md: 5.3 + 25.5 MB forward, 94.6 + 7.0 MB inverse), scaled to R
-                     "traffic": R * (5.3 + 25.5 + 94.6 + 7.0) * 1e6 / 128,
+                     # dram__bytes_read + dram__bytes_write of the kernel pair, ncu --set full capture of 512 recordings of this
+                     # workload (profiles/acq_r02_quad_ncu_summary.md: 21.0 + 277.7 MB forward, 339.0 + 22.6 MB inverse), scaled to R.
+                     # Against 21.6 MB of algorithmic bytes: the forward spectra (335 MB per 512 recordings, more than L2) are
+                     # written once and read back once; 31 GB/s, 0.5 % of HBM bandwidth.
+                     "traffic": R * (21.038336 + 277.677056 + 339.014144 + 22.628864) * 1e6 / 512,
                      "peak_source": f"measured in this run: register-resident FFMA chains on all SMs (gr_debug_fp32_peak); "
                                     f"theoretical at 1965 MHz = {FP32_PEAK_THEORY:.1f}",
-                     "traffic_source": "ncu --set full capture of 128 recordings (profiles/acq_r01_v8_ncu_summary.md), scaled to R",
+                     "traffic_source": "ncu --set full capture of 512 recordings, final kernels (profiles/acq_r02_quad_ncu_summary.md), scaled to R",
                      "flop_per_cell": FLOP_PER_CELL, "ms_per_launch": ms_kernel,
                      # what the kernels execute: 2 forward FFTs + wipe-offs per interval instead of the 41 the count credits
                      "flop_executed": R * (FLOP_PER_REC - (NBIN - 2) * NNONCOH * (F_FFT + TCOH * 2048 * 8)),
@@ -501,7 +503,13 @@ def run_b200(args):
             "e2e": {"value": world * f_recs * f_cells * args.steps / t_fe2e, "unit": "cells/s", "h2d_bytes_per_step": f_recs * f_rec_bytes,
                     "d2h_bytes_per_step": f_recs * NPRN * ACQ_BEST.itemsize, "api": "AcqPlan.search -> gr_acq_search_host (C ABI), pinned host buffers"},
             "roofline": {"bound": "fp32", "achieved": f_recs * f_flop / (ms_fine * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": f_recs * f_flop / (ms_fine * 1e-3) / 1e12 / fp32_peak, "flop_per_cell": f_flop / f_cells},
+                         "frac": f_recs * f_flop / (ms_fine * 1e-3) / 1e12 / fp32_peak, "flop_per_cell": f_flop / f_cells,
+                         "kernel": fplan.inverse_kernel() + " (+ acq_fwd_kernel, exact form: 15 % of the launch pair)",
+                         # ncu --set full of one 16-recording search (profiles/acq_r02_fine_ncu_summary.md, taken with the 4-CTA form
+                         # of the inverse kernel): forward 0.013 + 2.044 GB, inverse 2.156 + 0.013 GB, best 0.007 GB -- one spectrum per
+                         # bin, interval and recording (2.1 GB) written once and read once, against 13 MB of samples
+                         "traffic": f_recs * (0.013398 + 2.044471 + 2.155828 + 0.013175 + 0.006576) * 1e9 / 16,
+                         "traffic_source": "ncu capture (profiles/acq_r02_fine_ncu_summary.md), scaled by recordings"},
             "parity": fine_parity(fplan) if rank == 0 else None,
         }
         launches += (args.steps + 3) * 3 + (args.steps + 2) * 3
@@ -739,9 +747,10 @@ def run_b200(args):
                 "roofline": {"bound": "hbm", "kernel": "track_kernel", "achieved": (b_raw + b_out) / t_batch / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": (b_raw + b_out) / t_batch / 1e9 / hbm_peak,
                              # dram__bytes_read + dram__bytes_write of the kernel, ncu --set full capture of 400 epochs x 384
-                             # channels (profiles/track_r01_dense_ncu_summary.md: 17.0 + 16.9 MB), scaled to this launch
-                             "traffic": nb_ep * RB * TRACK_NCH * (17.009152 + 16.938496) * 1e6 / (400 * 384),
-                             "traffic_source": "ncu capture (profiles/), scaled by channel-epochs",
+                             # channels on 32 distinct recordings (profiles/track_r02_dense_exact_ncu_summary.md: 477.9 + 65.7 MB
+                             # against 488 MB of algorithmic bytes), scaled to this launch
+                             "traffic": nb_ep * RB * TRACK_NCH * (477.896192 + 65.671936) * 1e6 / (400 * 384),
+                             "traffic_source": "ncu capture of the exact dense form (profiles/track_r02_dense_exact_ncu_summary.md), scaled by channel-epochs",
                              "fp32_achieved_tflops": nb_ep * RB * TRACK_NCH * flop_ce / t_batch / 1e12, "fp32_peak_tflops": fp32_peak,
                              "note": "algorithmic bytes = each recording's raw I/Q once + one record per channel-epoch; the kernel is "
                                      "FP32/latency-bound (about 260 flop per byte, DESIGN.md 4.3), so the HBM fraction stays small by construction"},

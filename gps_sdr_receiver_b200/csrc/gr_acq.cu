@@ -47,6 +47,7 @@ struct gr_acq_plan {
     cudaEvent_t ev_in[GR_ACQ_HOST_CHUNKS];
     bool pipe_ready;
     int last_launches;
+    int force_quad;                               // -1: the form of the inverse kernel is chosen per call; 0 / 1: GPSB200_ACQ_QUAD at creation
     int last_inv_form;                            // GR_ACQ_INV_4CTA / GR_ACQ_INV_QUAD of the last run's inverse launches
     // The scratch above (d_spec, d_cells) belongs to the plan, so two *_dev calls of one plan must not overlap: a call on
     // another stream than the previous one first makes its stream wait for the event recorded behind the previous call.
@@ -1062,6 +1063,8 @@ extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* b
         const double argmax = 2.0 * 3.141592653589793 * fmax * (double)tcoh_ms * (double)nnoncoh * 1e-3;
         const char* e = getenv("GPSB200_ACQ_EXACT_NCO");
         p->exact_nco = e ? (atoi(e) != 0) : (argmax * 5.9604644775390625e-8 > 1e-4);
+        const char* q = getenv("GPSB200_ACQ_QUAD");              // form of the inverse kernel: chosen per call unless forced here
+        p->force_quad = q ? (atoi(q) != 0) : -1;
     }
     const int nb = gr_acq_classify_bins(bin_hz, nbins, getenv("GPSB200_ACQ_NOSHARE") == nullptr && !p->exact_nco, bin_base.data(),
                                         bin_shift.data(), base_f.data());
@@ -1151,16 +1154,14 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
                                                             : (one ? acq_fwd_kernel<GR_IN_CF32, true> : acq_fwd_kernel<GR_IN_CF32, false>);
     // development switch: GPSB200_ACQ_SCALAR=1 selects the scalar-FP32 form of the same transform (A/B timing)
     static const bool scalar_fp = getenv("GPSB200_ACQ_SCALAR") != nullptr;
-    // PRNs per work item of the 4-CTA form: 4, or 2 / 1 where smaller items shorten the last wave of a small launch (below)
-    void (*const inv_by_g[3])(const AcqArgs) = {acq_inv_kernel<1, 6, 4, true>, acq_inv_kernel<2, 6, 4, true>,
-                                                scalar_fp ? acq_inv_kernel<GR_ACQ_G, 6, 4, false> : acq_inv_kernel<GR_ACQ_G, 6, 4, true>};
+    void (*inv)(const AcqArgs) = scalar_fp ? acq_inv_kernel<GR_ACQ_G, 6, 4, false> : acq_inv_kernel<GR_ACQ_G, 6, 4, true>;
     const size_t fwd_smem = GR_FFT_SMEM_BYTES + (one ? 0 : (size_t)p->tcoh * sizeof(cf));
     if (fwd_smem > 200 * 1024) { gr_set_error("gr_acq_run_dev: tcoh too large"); return GR_ERR_ARG; }
     GR_CUDA(cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
     // development switch: GPSB200_ACQ_CTAS=2|3 pads the dynamic shared memory so that fewer CTAs fit an SM (occupancy study)
     static const int ctas_per_sm = getenv("GPSB200_ACQ_CTAS") ? atoi(getenv("GPSB200_ACQ_CTAS")) : 4;
     const int inv_smem = ctas_per_sm == 3 ? 72 * 1024 : ctas_per_sm == 2 ? 110 * 1024 : ctas_per_sm == 1 ? 200 * 1024 : GR_ACQ_INV_SMEM;
-    for (int i = 0; i < 3; ++i) GR_CUDA(cudaFuncSetAttribute(inv_by_g[i], cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem));
+    GR_CUDA(cudaFuncSetAttribute(inv, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem));
     const size_t bps = p->in_format == GR_IN_U8IQ ? 2 : 8;
     p->last_launches = 0;
     for (int r0 = 0; r0 < nrec; r0 += sub) {
@@ -1184,24 +1185,7 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         a.nrec = nr;
         a.nprn = p->nprn;
         a.nbins = p->nbins;
-        // Work items of the 4-CTA form = (recording, bin, G PRNs), G x nnoncoh transforms each, dealt round-robin to the resident
-        // CTAs: the launch lasts ceil(items / CTAs) items.  G = 4 unless smaller items shorten that (each item costs about a
-        // quarter of a transform on top: work-item change): e.g. a 51-bin shard of configs[3] on 16 recordings is 12 rounds of
-        // 80 transforms at G = 4 and 45 rounds of 20 at G = 1 (6 % less).
-        const long long n_cta = (long long)(ctas_per_sm >= 1 && ctas_per_sm <= 4 ? ctas_per_sm : 4) * gr_lib()->num_sms;
-        int gsel = GR_ACQ_G;
-        double t_std = 0.0;
-        for (int gg = GR_ACQ_G; gg >= 1; gg >>= 1) {
-            const long long items = (long long)nr * p->nbins * ((p->nprn + gg - 1) / gg);
-            const double tg = (double)((items + n_cta - 1) / n_cta) * ((double)(gg * p->nnoncoh) + 0.25);
-            if (gg == GR_ACQ_G || tg < 0.99 * t_std) { gsel = gg; t_std = tg; }
-        }
-        if (const char* g_env = getenv("GPSB200_ACQ_G")) {            // GPSB200_ACQ_G=1|2|4 forces the item size (read per call: the tests flip it)
-            const int gg = atoi(g_env);
-            if (gg == 1 || gg == 2 || gg == 4) gsel = gg;
-        }
-        if (scalar_fp) gsel = GR_ACQ_G;
-        a.ngroups = (p->nprn + gsel - 1) / gsel;
+        a.ngroups = (p->nprn + GR_ACQ_G - 1) / GR_ACQ_G;
         a.tcoh = p->tcoh;
         a.nnoncoh = p->nnoncoh;
         a.mode = p->mode;
@@ -1215,23 +1199,30 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         if (nchunks > p->nbase) nchunks = p->nbase;
         if (nchunks < 1) nchunks = 1;
         a.bins_per_chunk = (int)((p->nbase + nchunks - 1) / nchunks);
+        if (p->exact_nco && p->tcoh > 1) a.bins_per_chunk += a.bins_per_chunk & 1;      // that form takes its bins two at a time
         a.nchunks = (p->nbase + a.bins_per_chunk - 1) / a.bins_per_chunk;
         const long long nfwd = units * a.nchunks;
         const long long ninv = (long long)nr * p->nbins * a.ngroups;
         if (nfwd > 0x7fffffffLL || ninv > 0x7fffffffLL) { gr_set_error("gr_acq_run_dev: grid too large"); return GR_ERR_ARG; }
         fwd<<<(unsigned)nfwd, GR_FFT_THREADS, fwd_smem, s>>>(a);
-        // Form of the inverse kernel: the quad form (one 512-thread CTA per SM, four PRNs of a (recording, bin) unit sharing
-        // the staged spectra) is 4 - 5 % faster per transform on full launches (21.3 against 22.4 ms per 512 recordings,
-        // 5.41 against 5.63 ms per 128: gpurun_out/r02_quad_ab.log) but hands out work in units of all PRNs x all intervals;
-        // the 4-CTA form in items of 4 PRNs.  Pick the one with the shorter critical path in transform slots (the last wave
-        // of a small launch decides: 16 recordings 0.73 against 0.77 ms, 4 recordings 0.19 against 0.31 ms for the 4-CTA
-        // form); GPSB200_ACQ_QUAD=0 / 1 forces a form.
-        const char* quad_env = getenv("GPSB200_ACQ_QUAD");           // read per call: the tests flip it
+        // Form of the inverse kernel.  The quad form (one 512-thread CTA per SM, four PRNs of a (recording, bin) unit sharing
+        // the staged spectra) is 4 - 5 % faster per transform on launches that fill the GPU many times over (21.3 against
+        // 22.4 ms per 512 recordings of configs[1], 5.41 against 5.63 ms per 128: profiles/acq_r02_quad_ab.log), but it hands
+        // out work in units of all PRNs x all intervals on one CTA per SM, so its last wave costs a whole unit; the 4-CTA form
+        // works in items of 4 PRNs on four CTAs per SM, and the CTAs of a thinly occupied last wave run faster (one CTA alone on
+        // an SM runs at 58 % of the rate of four), so its tail is soft: about a quarter of an item.  Measured cross-overs
+        // (profiles/acq_r02_quad_ab.log, acq_r02_units_ab.log): 64 recordings of configs[1] equal, 16 recordings 0.73 (4-CTA)
+        // against 0.77 ms, a 51-bin shard of configs[3] on 16 recordings 2.05 against 2.16 ms.  Splitting the quad form's units
+        // by PRN rounds, or the 4-CTA form's items down to 1 PRN, was built and measured: no gain on small launches over the
+        // 4-CTA form as it is, and 5 % lost on large ones (registers of the quad kernel), so neither is kept.
+        // GPSB200_ACQ_QUAD=0 / 1 (read when the plan is created) forces a form.
         const long long nunits = (long long)nr * p->nbins;
         const long long sms = gr_lib()->num_sms;
+        const long long n_cta = (long long)(ctas_per_sm >= 1 && ctas_per_sm <= 4 ? ctas_per_sm : 4) * sms;
         const long long nrounds = (p->nprn + 3) / 4;
+        const double t_std = ((double)ninv / (double)n_cta + 0.25) * (double)(GR_ACQ_G * p->nnoncoh);
         const double t_quad = (double)((nunits + sms - 1) / sms) * (double)(nrounds * p->nnoncoh) * 0.95;
-        const bool quad = quad_env ? atoi(quad_env) != 0 : (ctas_per_sm == 4 && t_quad < t_std);
+        const bool quad = p->force_quad >= 0 ? p->force_quad != 0 : (ctas_per_sm == 4 && t_quad < t_std);
         p->last_inv_form = quad ? GR_ACQ_INV_QUAD : GR_ACQ_INV_4CTA;
         if (quad) {
             const long long qgrid = nunits < sms ? nunits : sms;
@@ -1241,7 +1232,7 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
             qk<<<(unsigned)qgrid, 512, qsmem, s>>>(a);
         } else {
         const long long ninv_grid = ninv < n_cta ? ninv : n_cta;
-        inv_by_g[gsel == 1 ? 0 : gsel == 2 ? 1 : 2]<<<(unsigned)ninv_grid, GR_FFT_THREADS, inv_smem, s>>>(a);
+        inv<<<(unsigned)ninv_grid, GR_FFT_THREADS, inv_smem, s>>>(a);
         }
         GR_CUDA(cudaGetLastError());
         p->last_launches += 2;

@@ -333,18 +333,10 @@ def test_quad_form_of_the_inverse_kernel_equals_the_4cta_form_bit_for_bit(gpu, m
             monkeypatch.setenv("GPSB200_ACQ_QUAD", quad)
             plan = AcqPlan(prns, bins, tcoh, k, mode)
             out[quad] = plan.run(raw, nrec=nrec)
+            assert plan.inverse_kernel() == ("acq_inv_quad_kernel" if quad == "1" else "acq_inv_kernel")
             plan.close()
-        monkeypatch.setenv("GPSB200_ACQ_QUAD", "0")
-        for gsz in ("1", "2"):                                  # the 4-CTA form with 1 or 2 PRNs per work item (small launches)
-            monkeypatch.setenv("GPSB200_ACQ_G", gsz)
-            plan = AcqPlan(prns, bins, tcoh, k, mode)
-            out["g" + gsz] = plan.run(raw, nrec=nrec)
-            assert plan.inverse_kernel() == "acq_inv_kernel"
-            plan.close()
-        monkeypatch.delenv("GPSB200_ACQ_G")
         monkeypatch.delenv("GPSB200_ACQ_QUAD")
         assert out["0"].tobytes() == out["1"].tobytes(), (len(prns), len(bins), tcoh, k)
-        assert out["0"].tobytes() == out["g1"].tobytes() and out["0"].tobytes() == out["g2"].tobytes(), (len(prns), len(bins), tcoh, k)
         c = out["1"]
         assert int(c["mx"][0, prns.index(3), int(np.argmax(c["z"][0, prns.index(3)]))]) in (133, 134)
 
