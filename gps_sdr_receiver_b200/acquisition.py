@@ -118,7 +118,7 @@ class AcqPlan:
 
     def inverse_kernel(self) -> str:
         """Name of the inverse kernel the last run launched (the launcher picks per call, include/gps_b200.h)."""
-        return "acq_inv_quad_kernel" if _capi.lib().gr_acq_last_inverse_form(self._h) else "acq_inv_kernel"
+        return ("acq_inv_kernel", "acq_inv_quad_kernel", "acq_inv_quad_kernel + acq_inv_kernel")[_capi.lib().gr_acq_last_inverse_form(self._h)]
 
     # ---- the search proper: one (PRN, Doppler bin, code phase, metric) tuple per recording and PRN ----
     def search(self, samples, nrec: int = 1, rec_stride: int | None = None, out: np.ndarray | None = None) -> np.ndarray:

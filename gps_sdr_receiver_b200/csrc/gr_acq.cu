@@ -67,6 +67,8 @@ struct AcqArgs {
     const int32_t* bin_shift;
     int nrec, nprn, nbins, nbase, ngroups, tcoh, nnoncoh, mode;
     int nchunks, bins_per_chunk;   // forward kernel: base bins per CTA
+    int quad_units;                // quad inverse kernel: it takes units 0 .. quad_units-1 of the nrec * nbins (recording, bin) units
+    int work0;                     // 4-CTA inverse kernel: it takes work items work0 .. nrec * nbins * ngroups - 1
     int exact_nco;                 // per-sample float32 phase arguments also for tcoh > 1 (see acq_fwd_kernel)
     int need_e1;                   // some bin has an odd shift: the forward kernel writes the second (one-bin shifted) copy too
     float scale;               // 1 / (tcoh * 2048)
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(GR_FFT_THREADS, MINB) acq_inv_kernel(const Acq
     const int t = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);       // warp-uniform for the compiler
     const int nwork = a.nrec * a.nbins * a.ngroups;
-    int work = blockIdx.x;                                     // host guarantees gridDim.x <= nwork
+    int work = a.work0 + blockIdx.x;                           // host guarantees work0 + gridDim.x <= nwork
 
     if (t == 0) mbar_init(&xbar, 1);
     if (t < 32) {
@@ -789,7 +791,7 @@ __global__ void __launch_bounds__(512, 1) acq_inv_quad_kernel(const AcqArgs a) {
     unsigned char* gsm = smem_raw + (size_t)g * (2 * GR_W_BUF1_BYTES);           // this group's two exchange-1 buffers
     float4* buf1 = reinterpret_cast<float4*>(gsm);
     unsigned char* stage0 = smem_raw + 4 * 2 * GR_W_BUF1_BYTES;                  // stage b at stage0 + b * 16 KiB
-    const int nunits = a.nrec * a.nbins;
+    const int nunits = a.quad_units;                            // the first quad_units of the nrec * nbins (recording, bin) units
     const int nrounds = (a.nprn + 3) >> 2;
     const int per_unit = nrounds * a.nnoncoh;                   // stage fills per unit
     const int my_units = ((int)blockIdx.x < nunits) ? (nunits - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -1064,7 +1066,7 @@ extern "C" int gr_acq_plan_create(const int32_t* prns, int nprn, const double* b
         const char* e = getenv("GPSB200_ACQ_EXACT_NCO");
         p->exact_nco = e ? (atoi(e) != 0) : (argmax * 5.9604644775390625e-8 > 1e-4);
         const char* q = getenv("GPSB200_ACQ_QUAD");              // form of the inverse kernel: chosen per call unless forced here
-        p->force_quad = q ? (atoi(q) != 0) : -1;
+        p->force_quad = q ? atoi(q) : -1;                        // 0: 4-CTA form, 1: quad form, 2: quad for the whole waves + 4-CTA for the rest
     }
     const int nb = gr_acq_classify_bins(bin_hz, nbins, getenv("GPSB200_ACQ_NOSHARE") == nullptr && !p->exact_nco, bin_base.data(),
                                         bin_shift.data(), base_f.data());
@@ -1215,27 +1217,41 @@ extern "C" int gr_acq_run_dev(gr_acq_plan* p, const void* d_samples, int nrec, i
         // against 0.77 ms, a 51-bin shard of configs[3] on 16 recordings 2.05 against 2.16 ms.  Splitting the quad form's units
         // by PRN rounds, or the 4-CTA form's items down to 1 PRN, was built and measured: no gain on small launches over the
         // 4-CTA form as it is, and 5 % lost on large ones (registers of the quad kernel), so neither is kept.
-        // GPSB200_ACQ_QUAD=0 / 1 (read when the plan is created) forces a form.
+        // Third choice: the quad form for the whole waves and the 4-CTA form for the units of the last, partial wave (one more
+        // launch on the same stream).  GPSB200_ACQ_QUAD=0 / 1 (read when the plan is created) forces a single form, =2 this split.
         const long long nunits = (long long)nr * p->nbins;
         const long long sms = gr_lib()->num_sms;
         const long long n_cta = (long long)(ctas_per_sm >= 1 && ctas_per_sm <= 4 ? ctas_per_sm : 4) * sms;
         const long long nrounds = (p->nprn + 3) / 4;
-        const double t_std = ((double)ninv / (double)n_cta + 0.25) * (double)(GR_ACQ_G * p->nnoncoh);
-        const double t_quad = (double)((nunits + sms - 1) / sms) * (double)(nrounds * p->nnoncoh) * 0.95;
-        const bool quad = p->force_quad >= 0 ? p->force_quad != 0 : (ctas_per_sm == 4 && t_quad < t_std);
-        p->last_inv_form = quad ? GR_ACQ_INV_QUAD : GR_ACQ_INV_4CTA;
-        if (quad) {
-            const long long qgrid = nunits < sms ? nunits : sms;
+        const double unit_q = (double)(nrounds * p->nnoncoh) * 0.95, item = (double)(GR_ACQ_G * p->nnoncoh);
+        auto t_4cta = [&](long long items) { return items > 0 ? ((double)items / (double)n_cta + 0.25) * item : 0.0; };
+        const double t_std = t_4cta(ninv);
+        const double t_quad = (double)((nunits + sms - 1) / sms) * unit_q;
+        // ... and both: the quad form for the whole waves, the 4-CTA form for the units of the last, partial one
+        const long long u_full = nunits / sms * sms;
+        const double t_both = (double)(u_full / sms) * unit_q + t_4cta((nunits - u_full) * a.ngroups) + 0.1 * item;
+        long long uq = 0;                                           // units that go to the quad form
+        if (p->force_quad >= 0) uq = p->force_quad == 1 ? nunits : p->force_quad == 2 ? u_full : 0;
+        else if (ctas_per_sm == 4) uq = (t_quad <= t_std && t_quad <= t_both) ? nunits : (t_both < t_std ? u_full : 0);
+        p->last_inv_form = uq == nunits ? GR_ACQ_INV_QUAD : uq == 0 ? GR_ACQ_INV_4CTA : GR_ACQ_INV_BOTH;
+        a.quad_units = (int)uq;
+        a.work0 = (int)(uq * a.ngroups);
+        if (uq > 0) {
+            const long long qgrid = uq < sms ? uq : sms;
             void (*qk)(const AcqArgs) = acq_inv_quad_kernel<4>;
             const int qsmem = GR_ACQ_QUAD_SMEM(4);
             GR_CUDA(cudaFuncSetAttribute(qk, cudaFuncAttributeMaxDynamicSharedMemorySize, qsmem));
             qk<<<(unsigned)qgrid, 512, qsmem, s>>>(a);
-        } else {
-        const long long ninv_grid = ninv < n_cta ? ninv : n_cta;
-        inv<<<(unsigned)ninv_grid, GR_FFT_THREADS, inv_smem, s>>>(a);
+            p->last_launches += 1;
+        }
+        if (uq < nunits) {
+            const long long items = ninv - a.work0;
+            const long long ninv_grid = items < n_cta ? items : n_cta;
+            inv<<<(unsigned)ninv_grid, GR_FFT_THREADS, inv_smem, s>>>(a);
+            p->last_launches += 1;
         }
         GR_CUDA(cudaGetLastError());
-        p->last_launches += 2;
+        p->last_launches += 1;
     }
     GR_CUDA(cudaEventRecord(p->ev_last, s));
     p->last_stream = s;

@@ -109,10 +109,12 @@ int gr_acq_last_launches(const gr_acq_plan* plan);
 /* Form of the inverse kernel the last run launched.  Both compute the same cells bit for bit; the launcher picks per call:
  * GR_ACQ_INV_4CTA = acq_inv_kernel, four 128-thread CTAs per SM, work handed out in items of 4 PRNs x all intervals;
  * GR_ACQ_INV_QUAD = acq_inv_quad_kernel, one 512-thread CTA per SM whose four groups share every staged forward spectrum,
- * work handed out per (recording, bin): faster on launches that fill the GPU many times over, slower on small ones.
- * Environment (read when the plan is created): GPSB200_ACQ_QUAD=0 / =1 forces a form. */
+ * work handed out per (recording, bin): faster on launches that fill the GPU many times over, slower on small ones;
+ * GR_ACQ_INV_BOTH = the quad form for the whole waves of the launch, then the 4-CTA form for the rest.
+ * Environment (read when the plan is created): GPSB200_ACQ_QUAD=0 / =1 / =2 forces a form. */
 #define GR_ACQ_INV_4CTA 0
 #define GR_ACQ_INV_QUAD 1
+#define GR_ACQ_INV_BOTH 2 /* quad form for the whole waves of the launch, 4-CTA form for the rest */
 int gr_acq_last_inverse_form(const gr_acq_plan* plan);
 
 /* The search result proper: for every recording and PRN the Doppler bin with the largest
