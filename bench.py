@@ -388,7 +388,7 @@ def run_b200(args):
     t_e2e = max_over_ranks(t_e2e)
     e2e_value = world * R * CELLS_PER_REC * args.steps / t_e2e
     assert np.array_equal(best_np["bin"], AcqPlan.best_from_tensor(plan.search_dev(bufs[(args.steps - 1) % 2], nrec=R))["bin"])
-    launches = args.steps * 3          # acq_fwd_kernel, acq_inv_kernel, acq_best_kernel per step
+    launches = args.steps * plan.launches()   # acq_fwd_kernel, inverse kernel (one or two launches, see gr_acq_run_dev), acq_best_kernel per step
     del bufs, cells_dev, host_in
 
     line = {
@@ -472,6 +472,8 @@ def run_b200(args):
             for i in range(args.steps):
                 plan.search_dev(fraw, nrec=f_recs, out=fbest_dev)
             g1.record()
+            plan.search_launches = plan.launches()              # kernel launches of one device search (gr_acq_last_launches)
+            plan.search_kernel = plan.inverse_kernel()
             barrier()
             windows.append((t_a, time.perf_counter()))
             return max_over_ranks(g0.elapsed_time(g1)) / args.steps
@@ -490,6 +492,7 @@ def run_b200(args):
         for i in range(args.steps):
             fplan.search(fhost.numpy(), nrec=f_recs, out=fbest_np)
         t_fe2e = time.perf_counter() - t_a
+        fhost_launches = fplan.launches()                       # one host search = its chunks' launches
         barrier()
         windows.append((t_a, time.perf_counter()))
         t_fe2e = max_over_ranks(t_fe2e)
@@ -504,7 +507,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": f_recs * NPRN * ACQ_BEST.itemsize, "api": "AcqPlan.search -> gr_acq_search_host (C ABI), pinned host buffers"},
             "roofline": {"bound": "fp32", "achieved": f_recs * f_flop / (ms_fine * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": f_recs * f_flop / (ms_fine * 1e-3) / 1e12 / fp32_peak, "flop_per_cell": f_flop / f_cells,
-                         "kernel": fplan.inverse_kernel() + " (+ acq_fwd_kernel, exact form: 15 % of the launch pair)",
+                         "kernel": fplan.search_kernel + " (+ acq_fwd_kernel, exact form: 15 % of the launches)",
                          # ncu --set full of one 16-recording search (profiles/acq_r02_fine_ncu_summary.md, taken with the 4-CTA form
                          # of the inverse kernel): forward 0.013 + 2.044 GB, inverse 2.156 + 0.013 GB, best 0.007 GB -- one spectrum per
                          # bin, interval and recording (2.1 GB) written once and read once, against 13 MB of samples
@@ -512,7 +515,7 @@ def run_b200(args):
                          "traffic_source": "ncu capture (profiles/acq_r02_fine_ncu_summary.md), scaled by recordings"},
             "parity": fine_parity(fplan) if rank == 0 else None,
         }
-        launches += (args.steps + 3) * 3 + (args.steps + 2) * 3
+        launches += (args.steps + 3) * fplan.search_launches + (args.steps + 2) * fhost_launches
         # the fast form forced on the same grid (shared spectra + block rotations): what the exact form costs, and how far
         # the fast form is from the reference at this |f| T
         os.environ["GPSB200_ACQ_EXACT_NCO"] = "0"
@@ -526,7 +529,7 @@ def run_b200(args):
                          "frac": f_recs * f_flop / (ms_fast * 1e-3) / 1e12 / fp32_peak},
             "parity": fine_parity(eplan) if rank == 0 else None,
         }
-        launches += (args.steps + 3) * 3
+        launches += (args.steps + 3) * eplan.search_launches
         eplan.close()
         fplan.close()
 
@@ -593,7 +596,7 @@ def run_b200(args):
                                    "overlapping the next step's search; all gathers complete inside the timed region), merged on every rank",
                        "recordings_per_step": f_recs, "bins_per_rank": len(mine), "cells_per_recording": f_cells},
         }
-        launches += (args.steps + args.warmup) * 3
+        launches += (args.steps + args.warmup) * splan.launches()
         splan.close()
         del sraw
         line["gpu_launches"] = launches
