@@ -343,6 +343,32 @@ def test_quad_form_of_the_inverse_kernel_equals_the_4cta_form_bit_for_bit(gpu, m
         assert int(c["mx"][0, prns.index(3), int(np.argmax(c["z"][0, prns.index(3)]))]) in (133, 134)
 
 
+def test_plans_larger_than_the_kernel_parameter_tables(gpu, monkeypatch):
+    """Plans of up to 64 PRNs x 1024 bins hand their PRN list and per-bin (base, shift) codes to the inverse kernel in the
+    kernel parameters; larger ones read them from device arrays.  A cell does not depend on the other bins of its plan, so
+    a 1 100-bin plan must reproduce, bit for bit, the cells a small plan computes for the same bins -- in all three launch
+    choices of the inverse kernel."""
+    from gps_sdr_receiver_b200 import synth
+    from gps_sdr_receiver_b200.acquisition import AcqPlan, GR_ACQ_POW
+    sats = [synth.Sat(prn=9, doppler=1310.0, delay=77.3, amp=0.1), synth.Sat(prn=21, doppler=-4270.0, delay=1999.6, amp=0.1)]
+    prns, k = [9, 21, 5], 2
+    raw = synth.make_iq(sats, 2 * k, seed=77)
+    big = [-5500.0 + 10.0 * b for b in range(1100)]
+    pick = [0, 1, 123, 681, 682, 1024, 1025, 1099]                        # 681: 1 310 Hz, 123: -4 270 Hz
+    small = AcqPlan(prns, [big[b] for b in pick], 1, k, GR_ACQ_POW)
+    ref = small.run(raw, nrec=2)
+    small.close()
+    for quad in ("0", "1", "2"):
+        monkeypatch.setenv("GPSB200_ACQ_QUAD", quad)
+        plan = AcqPlan(prns, big, 1, k, GR_ACQ_POW)
+        cells = plan.run(raw, nrec=2)
+        plan.close()
+        assert cells[:, :, pick].tobytes() == ref.tobytes(), quad
+        assert int(cells["mx"][0, 0, 681]) in (77, 78) and float(cells["z"][0, 0, 681]) > 6
+        assert abs(int(np.argmax(cells["z"][1, 1])) - 123) <= 40              # 2 ms of signal: the Doppler main lobe is +-250 Hz wide
+    monkeypatch.delenv("GPSB200_ACQ_QUAD")
+
+
 def test_ragged_and_invalid_inputs(gpu):
     from gps_sdr_receiver_b200 import _capi
     from gps_sdr_receiver_b200.acquisition import AcqPlan
