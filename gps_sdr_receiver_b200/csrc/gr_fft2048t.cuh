@@ -78,7 +78,12 @@ __device__ __forceinline__ void tm_round(uint32_t taddr, float* r) {
     tm_st_16x256b_x4(taddr, r);
     tm_st_16x256b_x4(taddr + (16u << 16), r + 16);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#ifdef GR_TMEM_X32      // build switch of an experiment (profiles/acq_r02_x32_ab.log): one 32-register fetch instead of two 16-register ones is
+                        // 0.7 % faster in the 4-CTA form and 7 % slower in the quad form (32 consecutive registers: spills at its 128-register cap)
+    tm_ld_32x32b_x32(taddr, r);
+#else
     tm_ld_32x32b_x16x2(taddr, r);
+#endif
 }
 
 // Exchange 2 + stage 3: v[k2] (stage-2 outputs, twiddled) -> v[2 k3 + h] = X[base + 128 (2 k3 + h)]
@@ -139,10 +144,15 @@ __device__ __forceinline__ void fftt_ex2_stage3_pk(uint32_t taddr, uint32_t tw_a
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     float wa[16], wb[16];
     asm volatile(
+#ifdef GR_TMEM_X32
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%66];\n"
+#else
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%64];\n"
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%65];\n"
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47}, [%66];\n"
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%67];\n"
+#endif
         "tcgen05.wait::ld.sync.aligned;\n"
         : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]),
           "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]), "=f"(r[17]), "=f"(r[18]),
