@@ -343,6 +343,34 @@ def test_quad_form_of_the_inverse_kernel_equals_the_4cta_form_bit_for_bit(gpu, m
         assert int(c["mx"][0, prns.index(3), int(np.argmax(c["z"][0, prns.index(3)]))]) in (133, 134)
 
 
+def test_repeated_launches_of_every_inverse_form_are_bit_identical(gpu, monkeypatch):
+    """The quad form hands its spectra to four groups through a ring of stages with mbarrier hand-overs, and the split launch
+    runs two kernels on one grid: a race there would be intermittent.  Repeated launches of all three forms on the BASELINE
+    configs[1] grid (37 recordings: 10 full waves of quad units + a remainder) must give the 4-CTA form's cells every time
+    (`tools/stress_inverse_forms.py` is the long version: 570 launches at 512 / 37 / 3 recordings, 0 mismatches)."""
+    import torch
+    from gps_sdr_receiver_b200 import synth
+    from gps_sdr_receiver_b200.acquisition import AcqPlan, GR_ACQ_POW
+    prns, bins, recs = list(range(1, 33)), [-10000.0 + 500.0 * b for b in range(41)], 37
+    sats = [synth.Sat(prn=3, doppler=2440.0, delay=133.4, amp=0.1), synth.Sat(prn=30, doppler=-1990.0, delay=0.2, amp=0.1)]
+    raw = synth.make_iq_dev(sats, recs * 10, noise_sigma=0.25, seed=5, device=0)
+    plans = {}
+    for q in ("0", "1", "2"):
+        monkeypatch.setenv("GPSB200_ACQ_QUAD", q)
+        plans[q] = AcqPlan(prns, bins, 1, 10, GR_ACQ_POW)
+    monkeypatch.delenv("GPSB200_ACQ_QUAD")
+    ref = plans["0"].run_dev(raw, nrec=recs).clone()
+    out = torch.empty_like(ref)
+    for q in ("0", "1", "2"):
+        for i in range(6):
+            out.zero_()
+            plans[q].run_dev(raw, nrec=recs, out=out)
+            assert torch.equal(out, ref), (q, i, int((out != ref).sum()))
+    assert plans["2"].inverse_kernel() == "acq_inv_quad_kernel + acq_inv_kernel"
+    for p_ in plans.values():
+        p_.close()
+
+
 def test_plans_larger_than_the_kernel_parameter_tables(gpu, monkeypatch):
     """Plans of up to 64 PRNs x 1024 bins hand their PRN list and per-bin (base, shift) codes to the inverse kernel in the
     kernel parameters; larger ones read them from device arrays.  A cell does not depend on the other bins of its plan, so
