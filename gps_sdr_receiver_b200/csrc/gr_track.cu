@@ -218,15 +218,26 @@ __device__ __forceinline__ void corr_and_stats(cf* F, const float2* __restrict__
                                                const cf* tw1, const cf* tw2, int t, TrackSmem* S) {
     // kSub: the 128 threads of this transform are the first half of a 256-thread CTA: named barrier 1 instead of barrier 0
     auto sync = [&]() { if (kSub) asm volatile("bar.sync 1, 128;" ::: "memory"); else __syncthreads(); };
-    fft2048<!kSub, 1, kOneBuf>(F, fftbuf, tw1, tw2, t);
+    // ONE FFT body run twice (forward, then the swap-form inverse) instead of two inlined copies: 1 100 fewer instructions per
+    // kernel.  The epoch is ~10 000 instructions of straight-line code and the CTAs of an SM are never in the same place, so the
+    // instruction cache is a shared resource here: 16.4 -> 15.8 us per epoch at 3 CTAs per SM, 9.09 -> 8.96 us for one recording
+    // (profiles/track_r02_onefft_ab.log); same arithmetic in the same order, records bit-identical.
     cf y[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float2 c = __ldg(cs + t + 128 * j);
-        y[j].x = F[j].x * c.y + F[j].y * c.x;      // swap form of the inverse transform
-        y[j].y = F[j].x * c.x - F[j].y * c.y;
+    for (int j = 0; j < 16; ++j) y[j] = F[j];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        fft2048<!kSub, 1, kOneBuf>(y, fftbuf, tw1, tw2, t);
+        if (pass == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float2 c = __ldg(cs + t + 128 * j);
+                const cf f = y[j];
+                y[j].x = f.x * c.y + f.y * c.x;      // swap form of the inverse transform
+                y[j].y = f.x * c.x - f.y * c.y;
+            }
+        }
     }
-    fft2048<!kSub, 1, kOneBuf>(y, fftbuf, tw1, tw2, t);
     float st[16];
     float s = 0.f, s2 = 0.f, mx = -1.f;
     int idx = 0;
